@@ -1,0 +1,116 @@
+/*
+ * srps_c_api.h -- C ABI of the B200-native SRmeetsPS outer loop (libsrps_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of nihalsid/SRmeetsPS-CUDA: the do-while body
+ * of SRPS::execute (SRmeetsPS-GPU/SRPS.cu:276-317) and the device operators it calls
+ * (SRmeetsPS-GPU/devicecalls.cuh:26-37).  Plain pointers and sizes only; no torch / thrust /
+ * cuSPARSE / cuBLAS types.  Host arrays use the reference's layouts:
+ *
+ *   column-major images: pixel (row i, col j) <-> i + j*h              Utilities.cpp:330,343
+ *   masked vectors: the npix mask pixels in ascending linear order      SRPS.cu:157-162
+ *   I   [n][c][npix]   SRPS.cu:223-232         s  [n][c][4]   SRPS.cu:209-217
+ *   rho [c][npix]      devicecalls.cu:133-149  N  [4][npix]   devicecalls.cu:194-223
+ *   z   [npix]         SRPS.cu:242-248         z0s [npixs]    SRPS.cu:237-239
+ *
+ * The one deliberate signature change against devicecalls.cuh: the CSR operands (Dx, Dy, KT) are
+ * gone -- geometry is (mask, h, w, sf) and the operators are matrix-free stencils.
+ *
+ * Every function returns 0 on success, a cudaError_t value (>0) for CUDA failures or a negative
+ * SRPS_E_* code; srps_last_error() gives the message.  A context is single-threaded, owns one
+ * device, one non-blocking stream and all device memory (no allocation inside the loop).
+ */
+#ifndef SRPS_C_API_H
+#define SRPS_C_API_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRPS_E_INVALID   (-1)   /* bad argument / unsupported configuration */
+#define SRPS_E_STATE     (-2)   /* call order (e.g. iterate before upload) */
+#define SRPS_E_NOMEM     (-3)
+
+/* albedo_mode */
+#define SRPS_ALBEDO_CLOSED_FORM 0   /* rho = At b / At A per pixel, fused into the stack pass */
+#define SRPS_ALBEDO_REFERENCE_CG 1  /* the reference's <=101-pass CG on the diagonal system (devicecalls.cu:531,540) */
+
+/* srps_download / srps_set_state selectors */
+#define SRPS_BUF_S    0   /* [n][c][4]    */
+#define SRPS_BUF_RHO  1   /* [c][npix]    */
+#define SRPS_BUF_Z    2   /* [npix]       */
+#define SRPS_BUF_N    3   /* [4][npix]    */
+#define SRPS_BUF_DZ   4   /* [npix]       */
+#define SRPS_BUF_Z0S  5   /* [npixs]      */
+
+typedef struct srps_ctx srps_ctx;
+
+/* Replaces the geometry half of DataHandler (Utilities.h:166-181) + Preferences::deviceId
+ * (Utilities.h:224-230). */
+typedef struct srps_problem {
+    int h, w;                    /* HR image rows / cols                       DataHandler::I_h, I_w */
+    int n_images;                /* n                                          DataHandler::I_n      */
+    int n_channels;              /* must be 3 (devicecalls.cu:615)             DataHandler::I_c      */
+    int sf;                      /* super-resolution factor, divides h and w   DataHandler::sf       */
+    float fx, fy, cx, cy;        /* K[0], K[4], K[6], K[7] of the column-major 3x3 K                 */
+    const unsigned char* mask;   /* host, h*w column-major, non-zero = inside  DataHandler::mask     */
+    int device;                  /* CUDA ordinal                               Preferences::deviceId */
+    int albedo_mode;             /* SRPS_ALBEDO_*                                                     */
+    int cg_max_iter;             /* 0 -> 100, the reference's max_iter (devicecalls.cu:231)           */
+    float cg_tol;                /* 0 -> 1e-9 (devicecalls.cu:230)                                    */
+} srps_problem;
+
+/* Per-phase device times (cudaEvent, ms) of the last srps_outer_iteration + launch counters. */
+typedef struct srps_timings {
+    float ms_lighting, ms_albedo, ms_depth, ms_normals, ms_total;
+    float ms_depth_cg;           /* the CG iterations alone (inside ms_depth) */
+    int cg_iters;                /* depth CG passes executed */
+    int albedo_cg_iters[3];
+    long long launches;          /* kernels launched by this context since creation */
+} srps_timings;
+
+/* Context: replaces cudaSetDevice + handle creation + all one-shot device setup of
+ * SRPS::execute (SRPS.cu:88-115, 151-203): mask indexing, LR mask, stencil-type map. */
+int  srps_ctx_create(const srps_problem* prob, srps_ctx** out);
+void srps_ctx_destroy(srps_ctx* ctx);
+const char* srps_last_error(const srps_ctx* ctx);   /* ctx may be NULL: last create error */
+int  srps_npix(const srps_ctx* ctx);                 /* imask.size()   SRPS.cu:167 */
+int  srps_npixs(const srps_ctx* ctx);                /* imasks.size()  SRPS.cu:168 */
+
+/* Loop-state upload from HOST buffers in the reference's masked layouts; initialises
+ * s=(0,0,-1,0), rho=0.5 and the first normals exactly as SRPS.cu:209-270.  I may be NULL if
+ * srps_upload_images_u8 is used instead. */
+int  srps_upload_state(srps_ctx* ctx, const float* I, const float* z, const float* z0s);
+/* Same stack as 8-bit samples (I = v/255, the image loader's arithmetic, Utilities.cpp:343). */
+int  srps_upload_images_u8(srps_ctx* ctx, const unsigned char* I8);
+/* Overwrite one state buffer from host (tests / resume).  After SRPS_BUF_Z call srps_normals. */
+int  srps_set_state(srps_ctx* ctx, int which, const float* host);
+int  srps_download(srps_ctx* ctx, int which, float* host);
+
+/* The four operators of the loop body, in the reference's order. */
+int  srps_lighting(srps_ctx* ctx);                                  /* cuda_based_lightning_estimation  devicecalls.cu:408-444 */
+int  srps_albedo(srps_ctx* ctx);                                    /* cuda_based_albedo_estimation     devicecalls.cu:513-548 */
+int  srps_depth(srps_ctx* ctx, float* energy, int* cg_iters);       /* cuda_based_depth_estimation      devicecalls.cu:636-786 */
+int  srps_normals(srps_ctx* ctx);                                   /* zx,zy + cuda_based_normal_init   SRPS.cu:310-315, devicecalls.cu:194-223 */
+
+/* One pass of the do-while body (SRPS.cu:276-317): lighting, albedo, depth (+energy), normals. */
+int  srps_outer_iteration(srps_ctx* ctx, float* energy, int* cg_iters);
+/* The whole loop with the reference's stop rule (SRPS.cu:298-301): stop when the energy rises,
+ * the relative change is < tol, or iteration > max_outer.  fixed_iters > 0 overrides the rule.
+ * energies (may be NULL) receives up to cap values; returns the number of passes in *n_done. */
+int  srps_run(srps_ctx* ctx, int max_outer, float tol, int fixed_iters, float* energies, int cap, int* n_done);
+
+int  srps_get_timings(const srps_ctx* ctx, srps_timings* out);
+int  srps_synchronize(srps_ctx* ctx);
+
+/* Test hook: y = (Kt K + G^T M G) p with the M of the current rho/dz/s (masked host vectors). */
+int  srps_apply_depth_operator(srps_ctx* ctx, const float* p_host, float* y_host);
+
+/* Build identification: "sm_100a;<git or date>" */
+const char* srps_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRPS_C_API_H */

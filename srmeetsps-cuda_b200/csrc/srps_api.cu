@@ -1,0 +1,693 @@
+// C ABI + context of the B200-native SRmeetsPS outer loop (see include/srps_c_api.h).
+//
+// Host side of the path SRPS::execute -> cuda_based_* (SRmeetsPS-GPU/SRPS.cu:276-317,
+// devicecalls.cuh:26-37).  Everything here is plumbing: geometry analysis of the mask (the
+// reference's CPU loops SRPS.cu:23-71,153-193), one allocation of every plane, kernel launches
+// on one non-blocking stream, and layout conversion at the boundary.  No cuBLAS / cuSPARSE /
+// Thrust, no CPU fallback: every operator is one of the kernels in srps_cg.cuh / srps_stack.cuh /
+// srps_epilogue.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/srps_c_api.h"
+#include "srps_cg.cuh"
+#include "srps_epilogue.cuh"
+#include "srps_stack.cuh"
+
+using namespace srps;
+
+static thread_local std::string g_create_error;
+
+struct srps_ctx {
+    srps_problem prob{};
+    Grid g{};
+    int npix = 0, npixs = 0, n = 0;
+    int device = 0, sm_count = 148;
+    bool full_rect = false;        // mask == its bounding box: uploads/downloads are plain 2-D copies
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8]{};
+    std::string err;
+    bool have_state = false, have_images = false, coeffs_valid = false, pending_normals = false;
+    long long launches = 0;
+    srps_timings tm{};
+
+    // device memory
+    float* plane_base = nullptr;   // all fp32 planes
+    long long n_planes = 0;
+    unsigned char* types_base = nullptr; unsigned char* types = nullptr;
+    unsigned char* lrmask = nullptr;
+    int* idx = nullptr; int* idx_lr = nullptr;
+    float* I = nullptr; float* I_base = nullptr;
+    float *z = nullptr, *r = nullptr, *p = nullptr, *y = nullptr, *e0 = nullptr, *dz = nullptr, *dz_new = nullptr;
+    float *w[3]{}, *gq[3]{}, *N[3]{}, *N_new[3]{}, *rho[3]{};
+    float *U = nullptr, *ad[3]{}, *ar[3]{}, *ap[3]{};    // reference-CG albedo only
+    float* z0lr = nullptr;
+    float* s = nullptr; float* gram = nullptr; LightConsts* lc = nullptr;
+    CgScalars* sc = nullptr;       // [4]: depth, albedo c=0..2
+    double* partials = nullptr; long long partials_len = 0;
+    unsigned* tickets = nullptr;   // [8]
+    double* energy = nullptr;      // [2]
+    void* staging = nullptr; size_t staging_bytes = 0;
+    // pinned host mirrors
+    double* h_energy = nullptr; CgScalars* h_sc = nullptr;
+    // launch geometry
+    int grid_stencil = 0, grid_update = 0, grid_stack = 0, grid_light_x = 0, light_groups = 0, grid_ep = 0, grid_al = 0, grid_gram = 0;
+    int tiles_x = 0, tiles_y = 0;
+    long long n4 = 0;
+    cudaGraphExec_t cg_graph = nullptr;
+    int use_graph = 1;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            char _b[512];                                                                          \
+            snprintf(_b, sizeof _b, "%s:%d: %s -> %s (%d)", __FILE__, __LINE__, #call, cudaGetErrorString(_e), (int)_e); \
+            ctx->err = _b;                                                                         \
+            return (int)_e;                                                                        \
+        }                                                                                          \
+    } while (0)
+
+#define LAUNCH(ctx, kern, grid, block, ...)                                  \
+    do {                                                                     \
+        kern<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);            \
+        (ctx)->launches++;                                                   \
+    } while (0)
+
+static int fail(srps_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+extern "C" const char* srps_build_info(void) { return "srps-b200 sm_100a " __DATE__ " " __TIME__; }
+extern "C" const char* srps_last_error(const srps_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+extern "C" int srps_npix(const srps_ctx* ctx) { return ctx ? ctx->npix : 0; }
+extern "C" int srps_npixs(const srps_ctx* ctx) { return ctx ? ctx->npixs : 0; }
+
+__global__ void light_consts_kernel(const float* s, int n, LightConsts* lc) { light_consts_from_s(s, n, lc, threadIdx.x, blockDim.x); }
+
+// ------------------------------------------------------------------------------------------------
+extern "C" void srps_ctx_destroy(srps_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->cg_graph) cudaGraphExecDestroy(ctx->cg_graph);
+    cudaFree(ctx->plane_base); cudaFree(ctx->types_base); cudaFree(ctx->lrmask); cudaFree(ctx->idx); cudaFree(ctx->idx_lr);
+    cudaFree(ctx->I_base); cudaFree(ctx->z0lr); cudaFree(ctx->s); cudaFree(ctx->gram); cudaFree(ctx->lc); cudaFree(ctx->sc);
+    cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->energy); cudaFree(ctx->staging); cudaFree(ctx->U);
+    cudaFreeHost(ctx->h_energy); cudaFreeHost(ctx->h_sc);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
+    const int h = prob->h, w = prob->w, sf = prob->sf;
+    ctx->prob = *prob;
+    ctx->prob.mask = nullptr;
+    ctx->n = prob->n_images;
+    ctx->device = prob->device;
+    CK(cudaSetDevice(ctx->device));
+    cudaDeviceProp dp;
+    CK(cudaGetDeviceProperties(&dp, ctx->device));
+    ctx->sm_count = dp.multiProcessorCount;
+    if (dp.major < 10) return fail(ctx, SRPS_E_INVALID, "this library is built for sm_100a (B200) only");
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->ev) CK(cudaEventCreate(&e));
+    const char* ug = getenv("SRPS_NO_GRAPH");
+    ctx->use_graph = (ug && ug[0] == '1') ? 0 : 1;
+
+    // ---- geometry of the mask (host, one-shot): bounding box rounded out to sf
+    const unsigned char* m = prob->mask;
+    int imin = h, imax = -1, jmin = w, jmax = -1;
+    long long npix = 0;
+    for (int j = 0; j < w; j++)
+        for (int i = 0; i < h; i++)
+            if (m[(size_t)i + (size_t)j * h]) {
+                npix++;
+                imin = std::min(imin, i); imax = std::max(imax, i);
+                jmin = std::min(jmin, j); jmax = std::max(jmax, j);
+            }
+    if (npix == 0) return fail(ctx, SRPS_E_INVALID, "empty mask");
+    Grid& g = ctx->g;
+    g.sf = sf;
+    g.ib0 = imin / sf * sf; g.jb0 = jmin / sf * sf;
+    const int ib1 = (imax + sf) / sf * sf, jb1 = (jmax + sf) / sf * sf;
+    g.nx = ib1 - g.ib0; g.ny = jb1 - g.jb0;
+    g.pitch = round_up(g.nx + 1, 32);
+    g.lnx = g.nx / sf; g.lny = g.ny / sf; g.lpitch = round_up(g.lnx, 4);
+    g.fx = prob->fx; g.fy = prob->fy; g.cx = prob->cx; g.cy = prob->cy;
+    g.plane = (long long)(g.ny + 2 * GUARD_LINES) * g.pitch;
+    if (g.plane >= (1ll << 31)) return fail(ctx, SRPS_E_INVALID, "grid too large for 32-bit pixel offsets");
+    ctx->npix = (int)npix;
+    ctx->n4 = (long long)g.ny * g.pitch / 4;
+    ctx->tiles_x = (g.nx + TX - 1) / TX;
+    ctx->tiles_y = (g.ny + TY - 1) / TY;
+    ctx->full_rect = (npix == (long long)g.nx * g.ny);
+
+    std::vector<unsigned char> types((size_t)g.plane, 0);
+    std::vector<int> idx((size_t)npix);
+    std::vector<unsigned char> lrmask((size_t)g.lny * g.lpitch, 0);
+    std::vector<int> idx_lr;
+    auto M = [&](int i, int j) -> bool { return i >= 0 && i < h && j >= 0 && j < w && m[(size_t)i + (size_t)j * h]; };
+    // LR mask: all sf*sf pixels inside (D*mask == 1, SRPS.cu:110-111); masked LR order = ascending r + q*(h/sf)
+    for (int bl = 0; bl < g.lny; bl++)
+        for (int bx = 0; bx < g.lnx; bx++) {
+            bool all = true;
+            for (int l = 0; l < sf && all; l++)
+                for (int k = 0; k < sf; k++)
+                    if (!M(g.ib0 + bx * sf + k, g.jb0 + bl * sf + l)) { all = false; break; }
+            if (all) { lrmask[(size_t)bl * g.lpitch + bx] = 1; idx_lr.push_back(bl * g.lpitch + bx); }
+        }
+    ctx->npixs = (int)idx_lr.size();
+    size_t pcount = 0;
+    for (int j = g.jb0; j < jb1 && j < w; j++)
+        for (int i = g.ib0; i < ib1 && i < h; i++) {
+            if (!M(i, j)) continue;
+            unsigned char t = T_MASK;
+            if (M(i, j + 1)) t |= T_XF; else if (M(i, j - 1)) t |= T_XB;        // SRPS.cu:39-46
+            if (M(i + 1, j)) t |= T_YF; else if (M(i - 1, j)) t |= T_YB;        // SRPS.cu:31-38
+            const int line = j - g.jb0, col = i - g.ib0;
+            if (lrmask[(size_t)(line / sf) * g.lpitch + col / sf]) t |= T_LR;
+            const long long off = (long long)line * g.pitch + col;
+            types[(size_t)(g.origin() + off)] = t;
+            idx[pcount++] = (int)off;
+        }
+
+    // ---- device memory: one allocation for all per-pixel fp32 planes
+    const bool refcg = prob->albedo_mode == SRPS_ALBEDO_REFERENCE_CG;
+    ctx->n_planes = 25 + (refcg ? 9 : 0);
+    CK(cudaMalloc(&ctx->plane_base, sizeof(float) * (size_t)(ctx->n_planes * g.plane)));
+    CK(cudaMemsetAsync(ctx->plane_base, 0, sizeof(float) * (size_t)(ctx->n_planes * g.plane), ctx->stream));
+    {
+        long long k = 0;
+        auto next = [&]() { return ctx->plane_base + (k++) * g.plane + g.origin(); };
+        ctx->z = next(); ctx->r = next(); ctx->p = next(); ctx->y = next(); ctx->e0 = next(); ctx->dz = next(); ctx->dz_new = next();
+        for (int c = 0; c < 3; c++) { ctx->w[c] = next(); ctx->gq[c] = next(); ctx->N[c] = next(); ctx->N_new[c] = next(); ctx->rho[c] = next(); }
+        k += 3;   // spare
+        if (refcg) for (int c = 0; c < 3; c++) { ctx->ad[c] = next(); ctx->ar[c] = next(); ctx->ap[c] = next(); }
+    }
+    if (refcg) {
+        CK(cudaMalloc(&ctx->U, sizeof(float) * (size_t)(15 * g.plane)));
+        CK(cudaMemsetAsync(ctx->U, 0, sizeof(float) * (size_t)(15 * g.plane), ctx->stream));
+    }
+    const size_t stack_floats = (size_t)ctx->n * 3 * (size_t)g.plane;
+    CK(cudaMalloc(&ctx->I_base, sizeof(float) * stack_floats));
+    CK(cudaMemsetAsync(ctx->I_base, 0, sizeof(float) * stack_floats, ctx->stream));
+    ctx->I = ctx->I_base + g.origin();
+    CK(cudaMalloc(&ctx->types_base, (size_t)g.plane));
+    CK(cudaMemcpyAsync(ctx->types_base, types.data(), (size_t)g.plane, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->types = ctx->types_base + g.origin();
+    CK(cudaMalloc(&ctx->lrmask, lrmask.size()));
+    CK(cudaMemcpyAsync(ctx->lrmask, lrmask.data(), lrmask.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMalloc(&ctx->idx, sizeof(int) * (size_t)npix));
+    CK(cudaMemcpyAsync(ctx->idx, idx.data(), sizeof(int) * (size_t)npix, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMalloc(&ctx->idx_lr, sizeof(int) * std::max<size_t>(1, idx_lr.size())));
+    if (!idx_lr.empty()) CK(cudaMemcpyAsync(ctx->idx_lr, idx_lr.data(), sizeof(int) * idx_lr.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMalloc(&ctx->z0lr, sizeof(float) * lrmask.size()));
+    CK(cudaMemsetAsync(ctx->z0lr, 0, sizeof(float) * lrmask.size(), ctx->stream));
+    CK(cudaMalloc(&ctx->s, sizeof(float) * (size_t)ctx->n * 12));
+    CK(cudaMalloc(&ctx->gram, sizeof(float) * 48));
+    CK(cudaMalloc(&ctx->lc, sizeof(LightConsts)));
+    CK(cudaMemsetAsync(ctx->lc, 0, sizeof(LightConsts), ctx->stream));
+    CK(cudaMalloc(&ctx->sc, sizeof(CgScalars) * 4));
+    CK(cudaMalloc(&ctx->tickets, sizeof(unsigned) * 8));
+    CK(cudaMemsetAsync(ctx->tickets, 0, sizeof(unsigned) * 8, ctx->stream));
+    CK(cudaMalloc(&ctx->energy, sizeof(double) * 2));
+    CK(cudaMallocHost(&ctx->h_energy, sizeof(double) * 2));
+    CK(cudaMallocHost(&ctx->h_sc, sizeof(CgScalars) * 4));
+    {
+        CgScalars init[4];
+        memset(init, 0, sizeof init);
+        const int mi = prob->cg_max_iter > 0 ? prob->cg_max_iter : 100;        // devicecalls.cu:231
+        const float tol = prob->cg_tol > 0.f ? prob->cg_tol : 1e-9f;           // devicecalls.cu:230
+        for (auto& s : init) { s.max_iter = mi; s.tol2 = tol * tol; }
+        memcpy(ctx->h_sc, init, sizeof init);
+        CK(cudaMemcpyAsync(ctx->sc, ctx->h_sc, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->staging_bytes = std::max<size_t>(sizeof(float) * (size_t)npix * 3, 1 << 20);
+    CK(cudaMalloc(&ctx->staging, ctx->staging_bytes));
+
+    // ---- launch geometry: persistent grids, a multiple of the SM count
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stencil_kernel<MODE_ITER>, CG_NT, 0));
+    ctx->grid_stencil = std::min(ctx->tiles_x * ctx->tiles_y, ctx->sm_count * std::max(1, occ));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_update_kernel, CG_NT, 0));
+    ctx->grid_update = (int)std::min<long long>((ctx->n4 + CG_NT - 1) / CG_NT, (long long)ctx->sm_count * std::max(1, occ));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stack_project_kernel<true>, ST_NT, 0));
+    ctx->grid_stack = (int)std::min<long long>((ctx->n4 + ST_NT - 1) / ST_NT, (long long)ctx->sm_count * std::max(1, occ));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lighting_reduce_kernel, ST_NT, 0));
+    ctx->light_groups = (ctx->n + LIGHT_IB - 1) / LIGHT_IB;
+    ctx->grid_light_x = (int)std::min<long long>((ctx->n4 + ST_NT - 1) / ST_NT,
+                                                 std::max(1, ctx->sm_count * std::max(1, occ) / ctx->light_groups));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lighting_gram_kernel, ST_NT, 0));
+    ctx->grid_gram = (int)std::min<long long>((ctx->n4 + ST_NT - 1) / ST_NT, (long long)ctx->sm_count * std::max(1, occ));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, normals_energy_kernel<true>, EP_NT, 0));
+    ctx->grid_ep = (int)std::min<long long>((ctx->n4 + EP_NT - 1) / EP_NT, (long long)ctx->sm_count * std::max(1, occ));
+    ctx->grid_al = (int)std::min<long long>((ctx->n4 + AL_NT - 1) / AL_NT, (long long)ctx->sm_count * 4);
+    long long pl = std::max<long long>({(long long)ctx->grid_stencil, (long long)ctx->grid_update, (long long)ctx->grid_ep,
+                                        3ll * ctx->grid_al, 30ll * ctx->grid_gram,
+                                        (long long)LIGHT_IB * 12 * ctx->grid_light_x * ctx->light_groups}) + 64;
+    ctx->partials_len = pl;
+    CK(cudaMalloc(&ctx->partials, sizeof(double) * (size_t)pl));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int srps_ctx_create(const srps_problem* prob, srps_ctx** out) {
+    if (!prob || !out) return fail(nullptr, SRPS_E_INVALID, "null argument");
+    *out = nullptr;
+    if (prob->n_channels != 3) return fail(nullptr, SRPS_E_INVALID, "n_channels must be 3 (reference: devicecalls.cu:615)");
+    if (prob->n_images < 1 || prob->n_images > MAX_IMAGES) return fail(nullptr, SRPS_E_INVALID, "n_images must be in [1, 64]");
+    if (prob->h < 1 || prob->w < 1 || !prob->mask) return fail(nullptr, SRPS_E_INVALID, "bad image size / mask");
+    const int sf = prob->sf;
+    if (!(sf == 1 || sf == 2 || sf == 4 || sf == 8 || sf == 16)) return fail(nullptr, SRPS_E_INVALID, "sf must be 1, 2, 4, 8 or 16");
+    if (prob->h % sf || prob->w % sf) return fail(nullptr, SRPS_E_INVALID, "h and w must be multiples of sf");
+    if (prob->albedo_mode != SRPS_ALBEDO_CLOSED_FORM && prob->albedo_mode != SRPS_ALBEDO_REFERENCE_CG)
+        return fail(nullptr, SRPS_E_INVALID, "bad albedo_mode");
+    srps_ctx* ctx = new srps_ctx();
+    int rc = ctx_create_impl(ctx, prob);
+    if (rc != 0) {
+        g_create_error = ctx->err;
+        srps_ctx_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion helpers
+// ------------------------------------------------------------------------------------------------
+static int scatter_from_host(srps_ctx* ctx, const float* host, float* dense_plane) {
+    const Grid& g = ctx->g;
+    if (ctx->full_rect) {
+        CK(cudaMemcpy2DAsync(dense_plane, sizeof(float) * g.pitch, host, sizeof(float) * g.nx, sizeof(float) * g.nx, g.ny,
+                             cudaMemcpyHostToDevice, ctx->stream));
+        return 0;
+    }
+    CK(cudaMemcpyAsync(ctx->staging, host, sizeof(float) * (size_t)ctx->npix, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, scatter_kernel, (ctx->npix + 255) / 256, 256, (const float*)ctx->staging, ctx->idx, dense_plane, ctx->npix);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int gather_to_host(srps_ctx* ctx, const float* dense_plane, float* host) {
+    const Grid& g = ctx->g;
+    if (ctx->full_rect) {
+        CK(cudaMemcpy2DAsync(host, sizeof(float) * g.nx, dense_plane, sizeof(float) * g.pitch, sizeof(float) * g.nx, g.ny,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+        return 0;
+    }
+    LAUNCH(ctx, gather_kernel, (ctx->npix + 255) / 256, 256, dense_plane, ctx->idx, (float*)ctx->staging, ctx->npix);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host, ctx->staging, sizeof(float) * (size_t)ctx->npix, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));      // staging is reused by the next call
+    return 0;
+}
+
+static int launch_normals(srps_ctx* ctx, bool energy, float* const* Nout, float* dzout) {
+    NormalsArgs a{};
+    a.g = ctx->g; a.types = ctx->types; a.z = ctx->z;
+    for (int c = 0; c < 3; c++) { a.N[c] = Nout[c]; a.w[c] = ctx->w[c]; a.gq[c] = ctx->gq[c]; }
+    a.dz = dzout; a.lc = ctx->lc; a.e0 = ctx->e0;
+    a.partials = ctx->partials; a.ticket = ctx->tickets + 0; a.energy_out = ctx->energy; a.n4 = ctx->n4;
+    if (energy) LAUNCH(ctx, normals_energy_kernel<true>, ctx->grid_ep, EP_NT, a);
+    else LAUNCH(ctx, normals_energy_kernel<false>, ctx->grid_ep, EP_NT, a);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int srps_upload_images_u8(srps_ctx* ctx, const unsigned char* I8) {
+    if (!ctx || !I8) return fail(ctx, SRPS_E_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    const Grid& g = ctx->g;
+    const int planes = ctx->n * 3;
+    const size_t per = (size_t)ctx->npix;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>(planes, ctx->staging_bytes / per));
+    for (int p0 = 0; p0 < planes; p0 += chunk) {
+        const int np = std::min(chunk, planes - p0);
+        CK(cudaMemcpyAsync(ctx->staging, I8 + (size_t)p0 * per, per * np, cudaMemcpyHostToDevice, ctx->stream));
+        for (int k = 0; k < np; k++)
+            LAUNCH(ctx, scatter_u8_kernel, (ctx->npix + 255) / 256, 256, (const unsigned char*)ctx->staging + (size_t)k * per,
+                   ctx->idx, ctx->I + (long long)(p0 + k) * g.plane, ctx->npix);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->have_images = true;
+    return 0;
+}
+
+extern "C" int srps_upload_state(srps_ctx* ctx, const float* I, const float* z, const float* z0s) {
+    if (!ctx || !z || !z0s) return fail(ctx, SRPS_E_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    const Grid& g = ctx->g;
+    if (I) {
+        const int planes = ctx->n * 3;
+        if (ctx->full_rect) {
+            for (int pl = 0; pl < planes; pl++)
+                CK(cudaMemcpy2DAsync(ctx->I + (long long)pl * g.plane, sizeof(float) * g.pitch, I + (size_t)pl * ctx->npix,
+                                     sizeof(float) * g.nx, sizeof(float) * g.nx, g.ny, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            const size_t per = sizeof(float) * (size_t)ctx->npix;
+            const int chunk = (int)std::max<size_t>(1, std::min<size_t>(planes, ctx->staging_bytes / per));
+            for (int p0 = 0; p0 < planes; p0 += chunk) {
+                const int np = std::min(chunk, planes - p0);
+                CK(cudaMemcpyAsync(ctx->staging, I + (size_t)p0 * ctx->npix, per * np, cudaMemcpyHostToDevice, ctx->stream));
+                for (int k = 0; k < np; k++)
+                    LAUNCH(ctx, scatter_kernel, (ctx->npix + 255) / 256, 256, (const float*)ctx->staging + (size_t)k * ctx->npix,
+                           ctx->idx, ctx->I + (long long)(p0 + k) * g.plane, ctx->npix);
+                CK(cudaGetLastError());
+                CK(cudaStreamSynchronize(ctx->stream));
+            }
+        }
+        ctx->have_images = true;
+    }
+    if (!ctx->have_images) return fail(ctx, SRPS_E_STATE, "no image stack uploaded");
+    int rc;
+    if ((rc = scatter_from_host(ctx, z, ctx->z))) return rc;
+    if (ctx->npixs > 0) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemcpyAsync(ctx->staging, z0s, sizeof(float) * (size_t)ctx->npixs, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(ctx, scatter_kernel, (ctx->npixs + 255) / 256, 256, (const float*)ctx->staging, ctx->idx_lr, ctx->z0lr, ctx->npixs);
+        CK(cudaGetLastError());
+    }
+    // s = (0,0,-1,0) per (i,c)   SRPS.cu:209-217 ; rho = 0.5   devicecalls.cu:133-149
+    std::vector<float> s0((size_t)ctx->n * 12, 0.f);
+    for (int e = 0; e < ctx->n * 3; e++) s0[(size_t)e * 4 + 2] = -1.f;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(ctx->s, s0.data(), sizeof(float) * s0.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    LAUNCH(ctx, light_consts_kernel, 1, 32, ctx->s, ctx->n, ctx->lc);
+    for (int c = 0; c < 3; c++)
+        LAUNCH(ctx, fill_masked_kernel, (ctx->npix + 255) / 256, 256, ctx->idx, ctx->rho[c], ctx->npix, 0.5f);
+    CK(cudaGetLastError());
+    // first normals: zx, zy, normal_init   SRPS.cu:264-270
+    if ((rc = launch_normals(ctx, false, ctx->N, ctx->dz))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_state = true;
+    ctx->coeffs_valid = false;
+    ctx->pending_normals = false;
+    return 0;
+}
+
+extern "C" int srps_set_state(srps_ctx* ctx, int which, const float* host) {
+    if (!ctx || !host) return fail(ctx, SRPS_E_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    int rc = 0;
+    switch (which) {
+        case SRPS_BUF_S:
+            CK(cudaMemcpyAsync(ctx->s, host, sizeof(float) * (size_t)ctx->n * 12, cudaMemcpyHostToDevice, ctx->stream));
+            LAUNCH(ctx, light_consts_kernel, 1, 32, ctx->s, ctx->n, ctx->lc);
+            CK(cudaGetLastError());
+            break;
+        case SRPS_BUF_RHO:
+            for (int c = 0; c < 3 && !rc; c++) { rc = scatter_from_host(ctx, host + (size_t)c * ctx->npix, ctx->rho[c]); if (!rc) CK(cudaStreamSynchronize(ctx->stream)); }
+            break;
+        case SRPS_BUF_Z: rc = scatter_from_host(ctx, host, ctx->z); ctx->pending_normals = false; break;
+        case SRPS_BUF_N:
+            for (int c = 0; c < 3 && !rc; c++) { rc = scatter_from_host(ctx, host + (size_t)c * ctx->npix, ctx->N[c]); if (!rc) CK(cudaStreamSynchronize(ctx->stream)); }
+            ctx->pending_normals = false;
+            break;
+        case SRPS_BUF_DZ: rc = scatter_from_host(ctx, host, ctx->dz); ctx->pending_normals = false; break;
+        case SRPS_BUF_Z0S:
+            CK(cudaMemcpyAsync(ctx->staging, host, sizeof(float) * (size_t)ctx->npixs, cudaMemcpyHostToDevice, ctx->stream));
+            LAUNCH(ctx, scatter_kernel, (ctx->npixs + 255) / 256, 256, (const float*)ctx->staging, ctx->idx_lr, ctx->z0lr, ctx->npixs);
+            CK(cudaGetLastError());
+            break;
+        default: return fail(ctx, SRPS_E_INVALID, "bad buffer selector");
+    }
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->coeffs_valid = false;
+    return 0;
+}
+
+extern "C" int srps_download(srps_ctx* ctx, int which, float* host) {
+    if (!ctx || !host) return fail(ctx, SRPS_E_INVALID, "null argument");
+    if (!ctx->have_state) return fail(ctx, SRPS_E_STATE, "no state uploaded");
+    CK(cudaSetDevice(ctx->device));
+    int rc = 0;
+    switch (which) {
+        case SRPS_BUF_S: CK(cudaMemcpyAsync(host, ctx->s, sizeof(float) * (size_t)ctx->n * 12, cudaMemcpyDeviceToHost, ctx->stream)); break;
+        case SRPS_BUF_RHO: for (int c = 0; c < 3 && !rc; c++) rc = gather_to_host(ctx, ctx->rho[c], host + (size_t)c * ctx->npix); break;
+        case SRPS_BUF_Z: rc = gather_to_host(ctx, ctx->z, host); break;
+        case SRPS_BUF_N:
+            for (int c = 0; c < 3 && !rc; c++) rc = gather_to_host(ctx, ctx->N[c], host + (size_t)c * ctx->npix);
+            if (!rc) { CK(cudaStreamSynchronize(ctx->stream)); for (int p = 0; p < ctx->npix; p++) host[(size_t)3 * ctx->npix + p] = 1.f; }   // devicecalls.cu:175
+            break;
+        case SRPS_BUF_DZ: rc = gather_to_host(ctx, ctx->dz, host); break;
+        case SRPS_BUF_Z0S:
+            LAUNCH(ctx, gather_kernel, (ctx->npixs + 255) / 256, 256, (const float*)ctx->z0lr, ctx->idx_lr, (float*)ctx->staging, ctx->npixs);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(host, ctx->staging, sizeof(float) * (size_t)ctx->npixs, cudaMemcpyDeviceToHost, ctx->stream));
+            break;
+        default: return fail(ctx, SRPS_E_INVALID, "bad buffer selector");
+    }
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the four operators
+// ------------------------------------------------------------------------------------------------
+static int apply_pending_normals(srps_ctx* ctx) {
+    if (ctx->pending_normals) {      // N, dz of the new z were produced by the depth epilogue: adopt them
+        for (int c = 0; c < 3; c++) std::swap(ctx->N[c], ctx->N_new[c]);
+        std::swap(ctx->dz, ctx->dz_new);
+        ctx->pending_normals = false;
+    }
+    return 0;
+}
+
+extern "C" int srps_lighting(srps_ctx* ctx) {
+    if (!ctx) return SRPS_E_INVALID;
+    if (!ctx->have_state) return fail(ctx, SRPS_E_STATE, "no state uploaded");
+    CK(cudaSetDevice(ctx->device));
+    GramArgs ga{};
+    LightArgs la{};
+    for (int c = 0; c < 3; c++) { ga.rho[c] = la.rho[c] = ctx->rho[c]; ga.N[c] = la.N[c] = ctx->N[c]; }
+    ga.n4 = la.n4 = ctx->n4;
+    ga.partials = ctx->partials; ga.ticket = ctx->tickets + 1; ga.gram = ctx->gram;
+    LAUNCH(ctx, lighting_gram_kernel, ctx->grid_gram, ST_NT, ga);
+    la.I = ctx->I; la.plane = ctx->g.plane; la.n_images = ctx->n;
+    la.partials = ctx->partials; la.ticket = ctx->tickets + 2; la.gram = ctx->gram; la.s = ctx->s; la.lc = ctx->lc;
+    la.max_iter = ctx->h_sc[0].max_iter; la.tol2 = ctx->h_sc[0].tol2;
+    LAUNCH(ctx, lighting_reduce_kernel, dim3(ctx->grid_light_x, ctx->light_groups), ST_NT, la);
+    CK(cudaGetLastError());
+    ctx->coeffs_valid = false;
+    return 0;
+}
+
+extern "C" int srps_albedo(srps_ctx* ctx) {
+    if (!ctx) return SRPS_E_INVALID;
+    if (!ctx->have_state) return fail(ctx, SRPS_E_STATE, "no state uploaded");
+    CK(cudaSetDevice(ctx->device));
+    const bool refcg = ctx->prob.albedo_mode == SRPS_ALBEDO_REFERENCE_CG;
+    ProjectArgs pa{};
+    pa.g = ctx->g; pa.I = ctx->I; pa.plane = ctx->g.plane; pa.n_images = ctx->n; pa.s = ctx->s; pa.lc = ctx->lc;
+    pa.types = ctx->types; pa.dz = ctx->dz; pa.e0 = ctx->e0; pa.U = ctx->U; pa.plane_u = ctx->g.plane; pa.n4 = ctx->n4;
+    for (int c = 0; c < 3; c++) { pa.N[c] = ctx->N[c]; pa.rho[c] = ctx->rho[c]; pa.w[c] = ctx->w[c]; pa.gq[c] = ctx->gq[c]; }
+    if (!refcg) {
+        LAUNCH(ctx, stack_project_kernel<true>, ctx->grid_stack, ST_NT, pa);
+        CK(cudaGetLastError());
+        ctx->coeffs_valid = true;
+        return 0;
+    }
+    pa.U = ctx->U + ctx->g.origin();
+    LAUNCH(ctx, stack_project_kernel<false>, ctx->grid_stack, ST_NT, pa);
+    AlbedoArgs aa{};
+    aa.lc = ctx->lc; aa.U = pa.U; aa.plane_u = ctx->g.plane; aa.n4 = ctx->n4;
+    for (int c = 0; c < 3; c++) { aa.N[c] = ctx->N[c]; aa.rho[c] = ctx->rho[c]; aa.d[c] = ctx->ad[c]; aa.r[c] = ctx->ar[c]; aa.p[c] = ctx->ap[c]; }
+    aa.sc = ctx->sc + 1; aa.partials = ctx->partials; aa.ticket = ctx->tickets + 3;
+    const dim3 grid(ctx->grid_al, 3);
+    LAUNCH(ctx, albedo_init_kernel, grid, AL_NT, aa);
+    const int passes = ctx->h_sc[0].max_iter + 1;
+    for (int k = 0; k < passes; k++) {
+        LAUNCH(ctx, albedo_dir_kernel, grid, AL_NT, aa);
+        LAUNCH(ctx, albedo_update_kernel, grid, AL_NT, aa);
+        if ((k & 7) == 7) {     // the diagonal CG stops after ~15 passes (r.r <= tol^2): poll instead of 101 no-op launch pairs
+            CK(cudaMemcpyAsync(ctx->h_sc + 1, ctx->sc + 1, sizeof(CgScalars) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (!ctx->h_sc[1].active && !ctx->h_sc[2].active && !ctx->h_sc[3].active) break;
+        }
+    }
+    CK(cudaMemcpyAsync(ctx->h_sc + 1, ctx->sc + 1, sizeof(CgScalars) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaGetLastError());
+    ctx->coeffs_valid = false;     // w, g, e0 are formed by srps_depth from U and the new albedo
+    return 0;
+}
+
+static int launch_cg_iterations(srps_ctx* ctx, const StencilArgs& sa, const UpdateArgs& ua, int passes) {
+    for (int k = 0; k < passes; k++) {
+        LAUNCH(ctx, stencil_kernel<MODE_ITER>, ctx->grid_stencil, CG_NT, sa);
+        LAUNCH(ctx, cg_update_kernel, ctx->grid_update, CG_NT, ua);
+    }
+    return 0;
+}
+
+static void fill_stencil_args(srps_ctx* ctx, StencilArgs& sa) {
+    sa.g = ctx->g; sa.types = ctx->types; sa.w0 = ctx->w[0]; sa.w1 = ctx->w[1]; sa.w2 = ctx->w[2]; sa.lc = ctx->lc;
+    sa.vin = ctx->z; sa.r = ctx->r; sa.p = ctx->p; sa.y = ctx->y; sa.g0 = ctx->gq[0]; sa.g1 = ctx->gq[1]; sa.g2 = ctx->gq[2];
+    sa.z0lr = ctx->z0lr; sa.sc = ctx->sc; sa.partials = ctx->partials; sa.ticket = ctx->tickets + 4;
+    sa.tiles_x = ctx->tiles_x; sa.tiles_y = ctx->tiles_y;
+}
+
+extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
+    if (!ctx) return SRPS_E_INVALID;
+    if (!ctx->have_state) return fail(ctx, SRPS_E_STATE, "no state uploaded");
+    CK(cudaSetDevice(ctx->device));
+    const bool refcg = ctx->prob.albedo_mode == SRPS_ALBEDO_REFERENCE_CG;
+    if (!ctx->coeffs_valid) {
+        if (!refcg) return fail(ctx, SRPS_E_STATE, "srps_depth needs srps_albedo first (closed-form mode forms w,g,e0 in the stack pass)");
+        CoeffArgs ca{};
+        ca.g = ctx->g; ca.lc = ctx->lc; ca.types = ctx->types; ca.U = ctx->U + ctx->g.origin(); ca.plane_u = ctx->g.plane;
+        ca.dz = ctx->dz; ca.e0 = ctx->e0; ca.n4 = ctx->n4;
+        for (int c = 0; c < 3; c++) { ca.rho[c] = ctx->rho[c]; ca.w[c] = ctx->w[c]; ca.gq[c] = ctx->gq[c]; }
+        LAUNCH(ctx, depth_coeffs_kernel, ctx->grid_al, AL_NT, ca);
+        CK(cudaGetLastError());
+        ctx->coeffs_valid = true;
+    }
+    StencilArgs sa{};
+    fill_stencil_args(ctx, sa);
+    // residual r = Kt z0s + At B - (KtK + AtA) z   devicecalls.cu:743-745,758  (written to `r`)
+    StencilArgs si = sa;
+    si.y = ctx->r;
+    LAUNCH(ctx, stencil_kernel<MODE_INIT>, ctx->grid_stencil, CG_NT, si);
+    CK(cudaGetLastError());
+    UpdateArgs ua{};
+    ua.x = ctx->z; ua.r = ctx->r; ua.p = ctx->p; ua.y = ctx->y; ua.n4 = ctx->n4; ua.sc = ctx->sc; ua.partials = ctx->partials;
+    ua.ticket = ctx->tickets + 5;
+    const int passes = ctx->h_sc[0].max_iter + 1;     // k <= max_iter -> max_iter + 1 passes   devicecalls.cu:252
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (ctx->use_graph) {
+        if (!ctx->cg_graph) {
+            cudaGraph_t graph = nullptr;
+            const long long before = ctx->launches;
+            CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            launch_cg_iterations(ctx, sa, ua, passes);
+            CK(cudaStreamEndCapture(ctx->stream, &graph));
+            ctx->launches = before;
+            CK(cudaGraphInstantiate(&ctx->cg_graph, graph, 0));
+            CK(cudaGraphDestroy(graph));
+        }
+        CK(cudaGraphLaunch(ctx->cg_graph, ctx->stream));
+        ctx->launches += 2ll * passes;
+    } else {
+        launch_cg_iterations(ctx, sa, ua, passes);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    // energy with lagged A,B and the new z (devicecalls.cu:762-767) + the normals of the new z
+    int rc;
+    if ((rc = launch_normals(ctx, true, ctx->N_new, ctx->dz_new))) return rc;
+    EnergyDepthArgs ea{};
+    ea.g = ctx->g; ea.z = ctx->z; ea.z0lr = ctx->z0lr; ea.lrmask = ctx->lrmask; ea.partials = ctx->partials + 0;
+    ea.ticket = ctx->tickets + 6; ea.energy_out = ctx->energy;
+    const long long ncell = (long long)ctx->g.lny * ctx->g.lnx;
+    LAUNCH(ctx, energy_depth_kernel, (int)std::min<long long>((ncell + EP_NT - 1) / EP_NT, ctx->sm_count * 4), EP_NT, ea);
+    CK(cudaGetLastError());
+    ctx->pending_normals = true;
+    CK(cudaMemcpyAsync(ctx->h_energy, ctx->energy, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_sc, ctx->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->tm.cg_iters = ctx->h_sc[0].k;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+    ctx->tm.ms_depth_cg = ms;
+    if (energy) *energy = (float)(ctx->h_energy[1] + ctx->h_energy[0]);     // t1 + lambda*t2, lambda = 1   devicecalls.cu:785
+    if (cg_iters) *cg_iters = ctx->h_sc[0].k;
+    return 0;
+}
+
+extern "C" int srps_normals(srps_ctx* ctx) {
+    if (!ctx) return SRPS_E_INVALID;
+    if (!ctx->have_state) return fail(ctx, SRPS_E_STATE, "no state uploaded");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->pending_normals) return apply_pending_normals(ctx);
+    return launch_normals(ctx, false, ctx->N, ctx->dz);
+}
+
+extern "C" int srps_outer_iteration(srps_ctx* ctx, float* energy, int* cg_iters) {
+    if (!ctx) return SRPS_E_INVALID;
+    int rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if ((rc = srps_lighting(ctx))) return rc;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if ((rc = srps_albedo(ctx))) return rc;
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if ((rc = srps_depth(ctx, energy, cg_iters))) return rc;
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    if ((rc = srps_normals(ctx))) return rc;
+    CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->tm.ms_lighting, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->tm.ms_albedo, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->tm.ms_depth, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->tm.ms_normals, ctx->ev[3], ctx->ev[6]);
+    cudaEventElapsedTime(&ctx->tm.ms_total, ctx->ev[0], ctx->ev[6]);
+    for (int c = 0; c < 3; c++) ctx->tm.albedo_cg_iters[c] = ctx->prob.albedo_mode == SRPS_ALBEDO_REFERENCE_CG ? ctx->h_sc[1 + c].k : 0;
+    return 0;
+}
+
+extern "C" int srps_run(srps_ctx* ctx, int max_outer, float tol, int fixed_iters, float* energies, int cap, int* n_done) {
+    if (!ctx) return SRPS_E_INVALID;
+    if (max_outer <= 0) max_outer = 10;      // SRPS.cu:86
+    if (tol <= 0.f) tol = 5e-3f;             // SRPS.cu:85
+    float last = NAN;
+    int iteration = 1;
+    bool stop = false;
+    do {
+        float e = 0.f;
+        int rc = srps_outer_iteration(ctx, &e, nullptr);
+        if (rc) return rc;
+        const float rel = fabsf(last - e) / fabsf(e);                              // SRPS.cu:298
+        if (e > last || rel < tol || iteration > max_outer) stop = true;           // SRPS.cu:299-301
+        if (fixed_iters > 0) stop = iteration >= fixed_iters;
+        last = e;
+        if (energies && iteration - 1 < cap) energies[iteration - 1] = e;
+        iteration++;
+    } while (!stop);
+    if (n_done) *n_done = iteration - 1;
+    return 0;
+}
+
+extern "C" int srps_get_timings(const srps_ctx* ctx, srps_timings* out) {
+    if (!ctx || !out) return SRPS_E_INVALID;
+    *out = ctx->tm;
+    out->launches = ctx->launches;
+    return 0;
+}
+
+extern "C" int srps_synchronize(srps_ctx* ctx) {
+    if (!ctx) return SRPS_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int srps_apply_depth_operator(srps_ctx* ctx, const float* p_host, float* y_host) {
+    if (!ctx || !p_host || !y_host) return fail(ctx, SRPS_E_INVALID, "null argument");
+    if (!ctx->coeffs_valid) return fail(ctx, SRPS_E_STATE, "depth coefficients not formed (call srps_albedo, and srps_depth in reference-CG mode)");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = scatter_from_host(ctx, p_host, ctx->p))) return rc;     // clobbers the CG work planes p, y
+    StencilArgs sa{};
+    fill_stencil_args(ctx, sa);
+    sa.vin = ctx->p;
+    LAUNCH(ctx, stencil_kernel<MODE_APPLY>, ctx->grid_stencil, CG_NT, sa);
+    CK(cudaGetLastError());
+    return gather_to_host(ctx, ctx->y, y_host);
+}

@@ -1,0 +1,539 @@
+// Passes over the image stack I[n][c] (the only O(n*c*npix) data of the loop) and the small
+// per-pixel kernels around them.
+//
+//   lighting_gram_kernel / lighting_reduce_kernel : replace cuda_based_lightning_estimation
+//       (SRmeetsPS-GPU/devicecalls.cu:408-444): K7 `A_for_lightning_estimation`, n*c cublasSgemm
+//       Gram products (identical for every image), n*c cublasSgemv, ~80 4-byte memcpys per (i,c) and
+//       a host-driven CG on a 4x4 "sparse" matrix -> ONE pass over the stack with register-blocked
+//       accumulators, a single-pass grid reduction and the 4x4 reference CG run by the last block.
+//   stack_project_kernel : U_p[c][k] = sum_j s_jc[k] I_jcp (and sum_j I^2) in ONE pass; its fused
+//       epilogue replaces cuda_based_albedo_estimation (devicecalls.cu:497-548: sgemm shading,
+//       (npix*n)-row CSR expansions, SpGEMM producing a diagonal, CG) and the dense B / a1,a2,a3
+//       planes of cuda_based_depth_estimation (devicecalls.cu:550-620) by per-pixel w, g, e0.
+#pragma once
+#include "srps_common.cuh"
+
+namespace srps {
+
+constexpr int ST_NT = 128;     // threads per CTA in the stack passes
+constexpr int LIGHT_IB = 8;    // images per CTA row in the lighting reduction
+constexpr int MAX_IMAGES = 64; // n_images limit (shared-memory copy of s)
+
+// ---------------------------------------------------------------------------------------------
+// generic multi-value single-pass grid reduction (values as float per thread, partials as double)
+// Returns true in the last block; totals[0..NV) then valid in shared memory `tot`.
+// ---------------------------------------------------------------------------------------------
+template <int NT, int NV>
+__device__ __forceinline__ bool grid_reduce_multi(const float (&v)[NV], double* partials, unsigned* ticket,
+                                                  double* tot /* smem [NV] */, float* wsm /* smem [NT/32][NV] */,
+                                                  int nblocks, int block_linear) {
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const float s = warp_sum(v[i]);
+        if (lane == 0) wsm[wid * NV + i] = s;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NV; i += NT) {
+        double b = 0.0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; w++) b += (double)wsm[w * NV + i];
+        partials[(long long)block_linear * NV + i] = b;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(ticket, 1u);
+        s_last = (t == (unsigned)nblocks - 1u);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    for (int i = threadIdx.x; i < NV; i += NT) {
+        double b = 0.0;
+        for (int blk = 0; blk < nblocks; blk++) b += __ldcg(partials + (long long)blk * NV + i);
+        tot[i] = b;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+    __syncthreads();
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gram matrices  AtA_c = sum_p rho_c^2 [N;1][N;1]^T       (devicecalls.cu:381,422)
+// ---------------------------------------------------------------------------------------------
+struct GramArgs {
+    const float* rho[3];
+    const float* N[3];
+    long long n4;
+    double* partials;      // [grid][30]
+    unsigned* ticket;
+    float* gram;           // out: [3][16] full symmetric 4x4 per channel
+};
+
+__global__ void __launch_bounds__(ST_NT, 4) lighting_gram_kernel(const GramArgs a) {
+    __shared__ double tot[30];
+    __shared__ float wsm[(ST_NT / 32) * 30];
+    float acc[30];
+#pragma unroll
+    for (int i = 0; i < 30; i++) acc[i] = 0.f;
+    const long long stride = (long long)gridDim.x * ST_NT;
+    for (long long i = (long long)blockIdx.x * ST_NT + threadIdx.x; i < a.n4; i += stride) {
+        const float4 n0 = ld4(a.N[0] + 4 * i), n1 = ld4(a.N[1] + 4 * i), n2 = ld4(a.N[2] + 4 * i);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float4 r = ld4(a.rho[c] + 4 * i);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float rr = f4get(r, k);
+                const float v[4] = {rr * f4get(n0, k), rr * f4get(n1, k), rr * f4get(n2, k), rr};
+                int q = 0;
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+#pragma unroll
+                    for (int y = x; y < 4; y++) acc[c * 10 + q++] += v[x] * v[y];
+            }
+        }
+    }
+    if (grid_reduce_multi<ST_NT, 30>(acc, a.partials, a.ticket, tot, wsm, gridDim.x, blockIdx.x)) {
+        if (threadIdx.x < 48) {
+            const int c = threadIdx.x / 16, e = threadIdx.x % 16, x = e / 4, y = e % 4;
+            const int lo = x < y ? x : y, hi = x < y ? y : x;
+            const int q = lo * 4 - (lo * (lo - 1)) / 2 + (hi - lo);     // index into the upper triangle
+            a.gram[c * 16 + e] = (float)tot[c * 10 + q];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stack pass 1: rhs_{i,c} = sum_p rho_c [N;1] I_icp  (devicecalls.cu:423), then -- in the last
+// block -- the warm-started 4x4 reference CG for every (i,c) (devicecalls.cu:424-437, :229-279)
+// and the per-iteration lighting constants S3/S4.
+// ---------------------------------------------------------------------------------------------
+struct LightArgs {
+    const float* I;        // stack base (origin-offset), plane stride `plane`
+    long long plane;
+    const float* rho[3];
+    const float* N[3];
+    long long n4;
+    int n_images;
+    double* partials;      // [gridDim.x*gridDim.y][96]
+    unsigned* ticket;
+    const float* gram;     // [3][16]
+    float* s;              // in/out [n][3][4]
+    LightConsts* lc;       // out
+    int max_iter; float tol2;
+};
+
+__device__ inline void cg4_reference(const float* A, float* x, float* b, int max_iter, float tol2) {
+    float p[4] = {0.f, 0.f, 0.f, 0.f}, om[4];
+    float r0 = 0.f, r1 = 0.f;
+    int k = 0;
+    for (int i = 0; i < 4; i++) r1 += b[i] * b[i];
+    while (r1 > tol2 && k <= max_iter) {
+        k++;
+        if (k == 1) { for (int i = 0; i < 4; i++) p[i] = b[i]; }
+        else { const float beta = r1 / r0; for (int i = 0; i < 4; i++) p[i] = beta * p[i] + b[i]; }
+        float dot = 0.f;
+        for (int i = 0; i < 4; i++) {
+            float o = 0.f;
+            for (int j = 0; j < 4; j++) o += A[i * 4 + j] * p[j];
+            om[i] = o;
+            dot += p[i] * o;
+        }
+        const float alpha = r1 / dot;
+        for (int i = 0; i < 4; i++) { x[i] += alpha * p[i]; b[i] -= alpha * om[i]; }
+        r0 = r1;
+        r1 = 0.f;
+        for (int i = 0; i < 4; i++) r1 += b[i] * b[i];
+    }
+}
+
+__device__ inline void light_consts_from_s(const float* s, int n, LightConsts* lc, int tid, int nt) {
+    // S4_c = sum_j s_jc s_jc^T (upper triangle, 10) ; S3_c = its leading 3x3 (6)
+    for (int e = tid; e < 30; e += nt) {
+        const int c = e / 10, q = e % 10;
+        int x = 0, y = 0, cnt = 0;
+        for (int xx = 0; xx < 4; xx++)
+            for (int yy = xx; yy < 4; yy++) { if (cnt == q) { x = xx; y = yy; } cnt++; }
+        float acc = 0.f;
+        for (int j = 0; j < n; j++) acc += s[(j * 3 + c) * 4 + x] * s[(j * 3 + c) * 4 + y];
+        lc->S4[c][q] = acc;
+        if (x < 3 && y < 3) {
+            const int q3 = x * 3 - (x * (x - 1)) / 2 + (y - x);
+            lc->S3[c][q3] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ST_NT, 2) lighting_reduce_kernel(const LightArgs a) {
+    __shared__ double tot[LIGHT_IB * 12];
+    __shared__ float wsm[(ST_NT / 32) * LIGHT_IB * 12];
+    const int group = blockIdx.y;
+    const int i0 = group * LIGHT_IB;
+    const int nimg = min(LIGHT_IB, a.n_images - i0);
+    float acc[LIGHT_IB * 12];
+#pragma unroll
+    for (int i = 0; i < LIGHT_IB * 12; i++) acc[i] = 0.f;
+    const long long stride = (long long)gridDim.x * ST_NT;
+    for (long long i = (long long)blockIdx.x * ST_NT + threadIdx.x; i < a.n4; i += stride) {
+        const float4 n0 = ld4(a.N[0] + 4 * i), n1 = ld4(a.N[1] + 4 * i), n2 = ld4(a.N[2] + 4 * i);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float4 r = ld4(a.rho[c] + 4 * i);
+            float4 v[LIGHT_IB];
+#pragma unroll
+            for (int ii = 0; ii < LIGHT_IB; ii++)
+                v[ii] = (ii < nimg) ? ld4_stream(a.I + ((long long)(i0 + ii) * 3 + c) * a.plane + 4 * i) : f4zero();
+            const float4 a0 = make_float4(r.x * n0.x, r.y * n0.y, r.z * n0.z, r.w * n0.w);
+            const float4 a1 = make_float4(r.x * n1.x, r.y * n1.y, r.z * n1.z, r.w * n1.w);
+            const float4 a2 = make_float4(r.x * n2.x, r.y * n2.y, r.z * n2.z, r.w * n2.w);
+#pragma unroll
+            for (int ii = 0; ii < LIGHT_IB; ii++) {
+                float* o = acc + (ii * 3 + c) * 4;
+                o[0] += v[ii].x * a0.x + v[ii].y * a0.y + v[ii].z * a0.z + v[ii].w * a0.w;
+                o[1] += v[ii].x * a1.x + v[ii].y * a1.y + v[ii].z * a1.z + v[ii].w * a1.w;
+                o[2] += v[ii].x * a2.x + v[ii].y * a2.y + v[ii].z * a2.z + v[ii].w * a2.w;
+                o[3] += v[ii].x * r.x + v[ii].y * r.y + v[ii].z * r.z + v[ii].w * r.w;
+            }
+        }
+    }
+    const int nblocks = gridDim.x * gridDim.y;
+    const int lin = blockIdx.y * gridDim.x + blockIdx.x;
+    if (!grid_reduce_multi<ST_NT, LIGHT_IB * 12>(acc, a.partials, a.ticket, tot, wsm, nblocks, lin)) return;
+    // ---- last block: `tot` holds the sum over ALL blocks of all groups (values of different groups
+    // were added together), so redo the per-group sums from the partials, then solve.
+    __shared__ float s_new[MAX_IMAGES * 12];
+    const int gx = gridDim.x;
+    for (int e = threadIdx.x; e < a.n_images * 12; e += ST_NT) {
+        const int img = e / 12, ck = e % 12;
+        const int grp = img / LIGHT_IB, ii = img % LIGHT_IB;
+        double b = 0.0;
+        for (int bx = 0; bx < gx; bx++) b += __ldcg(a.partials + ((long long)(grp * gx + bx)) * (LIGHT_IB * 12) + ii * 12 + ck);
+        s_new[e] = (float)b;          // Atb for (img, c = ck/4, k = ck%4)
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < a.n_images * 3; e += ST_NT) {
+        const int c = e % 3;
+        float A[16], x[4], b[4];
+        for (int t = 0; t < 16; t++) A[t] = a.gram[c * 16 + t];
+        for (int t = 0; t < 4; t++) x[t] = a.s[e * 4 + t];
+        for (int t = 0; t < 4; t++) {                         // residual Atb - AtA s   devicecalls.cu:424
+            float ax = 0.f;
+            for (int u = 0; u < 4; u++) ax += A[t * 4 + u] * x[u];
+            b[t] = s_new[e * 4 + t] - ax;
+        }
+        cg4_reference(A, x, b, a.max_iter, a.tol2);           // devicecalls.cu:437
+        for (int t = 0; t < 4; t++) a.s[e * 4 + t] = x[t];
+    }
+    __threadfence_block();
+    __syncthreads();
+    light_consts_from_s(a.s, a.n_images, a.lc, threadIdx.x, ST_NT);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-pixel algebra shared by the fused and the reference-CG albedo paths
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float quad4(const float* S /*10*/, float n0, float n1, float n2) {
+    // [n0 n1 n2 1] S4 [n0 n1 n2 1]^T with S = (00 01 02 03 11 12 13 22 23 33)
+    return n0 * (S[0] * n0 + 2.f * (S[1] * n1 + S[2] * n2 + S[3])) + n1 * (S[4] * n1 + 2.f * (S[5] * n2 + S[6])) +
+           n2 * (S[7] * n2 + 2.f * S[8]) + S[9];
+}
+
+// w_c = (rho_c/dz)^2, g = sum_{c,j} t_cj B_cj, e0 = sum_{c,j} B_cj^2 from U, II   
+__device__ __forceinline__ void depth_coeffs_px(const LightConsts& lc, const float U[3][4], const float II[3],
+                                                const float rho[3], float dz, float fx, float fy, float xx, float yy,
+                                                float w[3], float g[3], float& e0) {
+    float gv0 = 0.f, gv1 = 0.f, gv2 = 0.f;
+    e0 = 0.f;
+    const float idz = 1.f / dz;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float rd = rho[c] * idz;
+        w[c] = rd * rd;
+        gv0 += rd * (U[c][0] - rho[c] * lc.S4[c][3]);
+        gv1 += rd * (U[c][1] - rho[c] * lc.S4[c][6]);
+        gv2 += rd * (U[c][2] - rho[c] * lc.S4[c][8]);
+        e0 += II[c] - 2.f * rho[c] * U[c][3] + rho[c] * rho[c] * lc.S4[c][9];
+    }
+    g[0] = fx * gv0 - xx * gv2;
+    g[1] = fy * gv1 - yy * gv2;
+    g[2] = -gv2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stack pass 2: U, II and (FUSED) closed-form albedo + depth coefficients
+// ---------------------------------------------------------------------------------------------
+struct ProjectArgs {
+    Grid g;
+    const float* I; long long plane; int n_images;
+    const float* s;               // [n][3][4] (device)
+    const LightConsts* lc;
+    const unsigned char* types;
+    const float* N[3]; const float* dz;
+    float* rho[3];                // FUSED: in (fallback) / out
+    float* w[3]; float* gq[3]; float* e0;     // FUSED: out
+    float* U;                     // !FUSED: out 15 planes (U[c][k] at plane c*4+k, II[c] at 12+c), stride plane_u
+    long long plane_u;
+    long long n4;
+};
+
+template <bool FUSED>
+__global__ void __launch_bounds__(ST_NT, 3) stack_project_kernel(const ProjectArgs a) {
+    __shared__ float4 s_sm[MAX_IMAGES * 3];
+    for (int e = threadIdx.x; e < a.n_images * 3; e += ST_NT) s_sm[e] = *reinterpret_cast<const float4*>(a.s + 4 * e);
+    __syncthreads();
+    const LightConsts lc = *a.lc;
+    const Grid& g = a.g;
+    const long long stride = (long long)gridDim.x * ST_NT;
+    const int q_per_line = g.pitch / 4;
+    for (long long i = (long long)blockIdx.x * ST_NT + threadIdx.x; i < a.n4; i += stride) {
+        float4 U[3][4], II[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            II[c] = f4zero();
+#pragma unroll
+            for (int k = 0; k < 4; k++) U[c][k] = f4zero();
+        }
+        const float* base = a.I + 4 * i;
+#pragma unroll 2
+        for (int j = 0; j < a.n_images; j++) {
+            float4 v[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) v[c] = ld4_stream(base + ((long long)j * 3 + c) * a.plane);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float4 sv = s_sm[j * 3 + c];
+                const float sk[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    U[c][k].x += sk[k] * v[c].x; U[c][k].y += sk[k] * v[c].y;
+                    U[c][k].z += sk[k] * v[c].z; U[c][k].w += sk[k] * v[c].w;
+                }
+                II[c].x += v[c].x * v[c].x; II[c].y += v[c].y * v[c].y;
+                II[c].z += v[c].z * v[c].z; II[c].w += v[c].w * v[c].w;
+            }
+        }
+        if (!FUSED) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) st4(a.U + (long long)(c * 4 + k) * a.plane_u + 4 * i, U[c][k]);
+                st4(a.U + (long long)(12 + c) * a.plane_u + 4 * i, II[c]);
+            }
+            continue;
+        }
+        // ---- fused epilogue: closed-form albedo (the fixed point of the reference's diagonal CG,
+        //      devicecalls.cu:531,540), then w, g, e0 with the NEW albedo (devicecalls.cu:550-620)
+        const long long line = i / q_per_line;
+        const int x = (int)(i - line * q_per_line) * 4;
+        const uchar4 t4 = *reinterpret_cast<const uchar4*>(a.types + 4 * i);
+        const unsigned char tv[4] = {t4.x, t4.y, t4.z, t4.w};
+        const float4 n0 = ld4(a.N[0] + 4 * i), n1 = ld4(a.N[1] + 4 * i), n2 = ld4(a.N[2] + 4 * i), dz4 = ld4(a.dz + 4 * i);
+        const float4 ro0 = ld4(a.rho[0] + 4 * i), ro1 = ld4(a.rho[1] + 4 * i), ro2 = ld4(a.rho[2] + 4 * i);
+        const float xx = (float)(g.jb0 + (int)line) - g.cx;
+        float4 orho[3], ow[3], og[3], oe = f4zero();
+#pragma unroll
+        for (int c = 0; c < 3; c++) { orho[c] = f4zero(); ow[c] = f4zero(); og[c] = f4zero(); }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!(tv[k] & T_MASK)) continue;
+            const float N0 = f4get(n0, k), N1 = f4get(n1, k), N2 = f4get(n2, k), dz = f4get(dz4, k);
+            const float rold[3] = {f4get(ro0, k), f4get(ro1, k), f4get(ro2, k)};
+            float Up[3][4], IIp[3], rho[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) Up[c][kk] = f4get(U[c][kk], k);
+                IIp[c] = f4get(II[c], k);
+                const float d = quad4(lc.S4[c], N0, N1, N2);
+                const float b = N0 * Up[c][0] + N1 * Up[c][1] + N2 * Up[c][2] + Up[c][3];
+                rho[c] = d > 0.f ? b / d : rold[c];
+            }
+            const float yy = (float)(g.ib0 + x + k) - g.cy;
+            float w[3], gg[3], e0;
+            depth_coeffs_px(lc, Up, IIp, rho, dz, g.fx, g.fy, xx, yy, w, gg, e0);
+#pragma unroll
+            for (int c = 0; c < 3; c++) { f4set(orho[c], k, rho[c]); f4set(ow[c], k, w[c]); f4set(og[c], k, gg[c]); }
+            f4set(oe, k, e0);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            st4(a.rho[c] + 4 * i, orho[c]);
+            st4(a.w[c] + 4 * i, ow[c]);
+            st4(a.gq[c] + 4 * i, og[c]);
+        }
+        st4(a.e0 + 4 * i, oe);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reference-faithful albedo: CG on the diagonal systems of the three channels at once
+// (devicecalls.cu:513-548 with :229-279).  blockIdx.y = channel; one CgScalars per channel.
+// ---------------------------------------------------------------------------------------------
+constexpr int AL_NT = 256;
+
+struct AlbedoArgs {
+    const LightConsts* lc;
+    const float* U; long long plane_u;      // U[c][k] planes from stack_project_kernel<false>
+    const float* N[3];
+    float* rho[3];
+    float* d[3]; float* r[3]; float* p[3];
+    long long n4;
+    CgScalars* sc;            // [3]
+    double* partials;         // [3][gridDim.x]
+    unsigned* ticket;         // [3]
+};
+
+// d = sum_i (N.s_ic)^2, b = sum_i (N.s_ic) I_icp, r = b - d rho, r1 = r.r   (devicecalls.cu:395-406,251)
+__global__ void __launch_bounds__(AL_NT, 4) albedo_init_kernel(const AlbedoArgs a) {
+    __shared__ double red[AL_NT / 32];
+    const int c = blockIdx.y;
+    const LightConsts lc = *a.lc;
+    double acc = 0.0;
+    const long long stride = (long long)gridDim.x * AL_NT;
+    for (long long i = (long long)blockIdx.x * AL_NT + threadIdx.x; i < a.n4; i += stride) {
+        const float4 n0 = ld4(a.N[0] + 4 * i), n1 = ld4(a.N[1] + 4 * i), n2 = ld4(a.N[2] + 4 * i);
+        const float4 u0 = ld4(a.U + (long long)(c * 4 + 0) * a.plane_u + 4 * i);
+        const float4 u1 = ld4(a.U + (long long)(c * 4 + 1) * a.plane_u + 4 * i);
+        const float4 u2 = ld4(a.U + (long long)(c * 4 + 2) * a.plane_u + 4 * i);
+        const float4 u3 = ld4(a.U + (long long)(c * 4 + 3) * a.plane_u + 4 * i);
+        const float4 ro = ld4(a.rho[c] + 4 * i);
+        float4 d4, r4;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float N0 = f4get(n0, k), N1 = f4get(n1, k), N2 = f4get(n2, k);
+            // out-of-mask cells have N = 0 and U = 0: d = S4[3][3] > 0 but b = 0 and rho = 0 -> r = 0
+            const float d = quad4(lc.S4[c], N0, N1, N2);
+            const float b = N0 * f4get(u0, k) + N1 * f4get(u1, k) + N2 * f4get(u2, k) + f4get(u3, k);
+            const float r = b - d * f4get(ro, k);
+            f4set(d4, k, d);
+            f4set(r4, k, r);
+            acc += (double)(r * r);
+        }
+        st4(a.d[c] + 4 * i, d4);
+        st4(a.r[c] + 4 * i, r4);
+        st4(a.p[c] + 4 * i, f4zero());
+    }
+    double total;
+    if (grid_reduce_last<AL_NT>(acc, a.partials + (long long)c * gridDim.x, a.ticket + c, red, total)) {
+        if (threadIdx.x == 0) {
+            CgScalars* s = a.sc + c;
+            s->r1 = total; s->r0 = 0.0; s->k = 0; s->beta = 0.f; s->alpha = 0.f;
+            s->active = ((float)total > s->tol2) && (0 <= s->max_iter);
+        }
+    }
+}
+
+// p = r + beta p ; dot = p.(d p) ; alpha = r1/dot          (devicecalls.cu:256-269)
+__global__ void __launch_bounds__(AL_NT, 4) albedo_dir_kernel(const AlbedoArgs a) {
+    __shared__ double red[AL_NT / 32];
+    const int c = blockIdx.y;
+    CgScalars* s = a.sc + c;
+    if (!s->active) return;
+    const float beta = s->beta;
+    double acc = 0.0;
+    const long long stride = (long long)gridDim.x * AL_NT;
+    for (long long i = (long long)blockIdx.x * AL_NT + threadIdx.x; i < a.n4; i += stride) {
+        const float4 r4 = ld4(a.r[c] + 4 * i), d4 = ld4(a.d[c] + 4 * i);
+        float4 p4 = ld4(a.p[c] + 4 * i);
+        p4.x = r4.x + beta * p4.x; p4.y = r4.y + beta * p4.y; p4.z = r4.z + beta * p4.z; p4.w = r4.w + beta * p4.w;
+        st4(a.p[c] + 4 * i, p4);
+        acc += (double)(p4.x * (d4.x * p4.x) + p4.y * (d4.y * p4.y)) + (double)(p4.z * (d4.z * p4.z) + p4.w * (d4.w * p4.w));
+    }
+    double total;
+    if (grid_reduce_last<AL_NT>(acc, a.partials + (long long)c * gridDim.x, a.ticket + c, red, total)) {
+        if (threadIdx.x == 0) { s->dot = total; s->alpha = (float)s->r1 / (float)total; }
+    }
+}
+
+// rho += alpha p ; r -= alpha d p ; r1 = r.r ; beta, k, active   (devicecalls.cu:270-274,252,262)
+__global__ void __launch_bounds__(AL_NT, 4) albedo_update_kernel(const AlbedoArgs a) {
+    __shared__ double red[AL_NT / 32];
+    const int c = blockIdx.y;
+    CgScalars* s = a.sc + c;
+    if (!s->active) return;
+    const float alpha = s->alpha;
+    double acc = 0.0;
+    const long long stride = (long long)gridDim.x * AL_NT;
+    for (long long i = (long long)blockIdx.x * AL_NT + threadIdx.x; i < a.n4; i += stride) {
+        const float4 p4 = ld4(a.p[c] + 4 * i), d4 = ld4(a.d[c] + 4 * i);
+        float4 x4 = ld4(a.rho[c] + 4 * i), r4 = ld4(a.r[c] + 4 * i);
+        x4.x += alpha * p4.x; x4.y += alpha * p4.y; x4.z += alpha * p4.z; x4.w += alpha * p4.w;
+        r4.x -= alpha * (d4.x * p4.x); r4.y -= alpha * (d4.y * p4.y); r4.z -= alpha * (d4.z * p4.z); r4.w -= alpha * (d4.w * p4.w);
+        st4(a.rho[c] + 4 * i, x4);
+        st4(a.r[c] + 4 * i, r4);
+        acc += (double)(r4.x * r4.x + r4.y * r4.y) + (double)(r4.z * r4.z + r4.w * r4.w);
+    }
+    double total;
+    if (grid_reduce_last<AL_NT>(acc, a.partials + (long long)c * gridDim.x, a.ticket + c, red, total)) {
+        if (threadIdx.x == 0) {
+            s->r0 = s->r1;
+            s->r1 = total;
+            s->k += 1;
+            s->beta = (float)total / (float)s->r0;
+            s->active = ((float)total > s->tol2) && (s->k <= s->max_iter);
+        }
+    }
+}
+
+// w, g, e0 from the stored U / II and the (CG-updated) albedo       (devicecalls.cu:550-620)
+struct CoeffArgs {
+    Grid g;
+    const LightConsts* lc;
+    const unsigned char* types;
+    const float* U; long long plane_u;
+    const float* rho[3]; const float* dz;
+    float* w[3]; float* gq[3]; float* e0;
+    long long n4;
+};
+
+__global__ void __launch_bounds__(AL_NT, 2) depth_coeffs_kernel(const CoeffArgs a) {
+    const LightConsts lc = *a.lc;
+    const Grid& g = a.g;
+    const int q_per_line = g.pitch / 4;
+    const long long stride = (long long)gridDim.x * AL_NT;
+    for (long long i = (long long)blockIdx.x * AL_NT + threadIdx.x; i < a.n4; i += stride) {
+        const long long line = i / q_per_line;
+        const int x = (int)(i - line * q_per_line) * 4;
+        const uchar4 t4 = *reinterpret_cast<const uchar4*>(a.types + 4 * i);
+        const unsigned char tv[4] = {t4.x, t4.y, t4.z, t4.w};
+        float4 U[3][4], II[3], ro[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) U[c][k] = ld4(a.U + (long long)(c * 4 + k) * a.plane_u + 4 * i);
+            II[c] = ld4(a.U + (long long)(12 + c) * a.plane_u + 4 * i);
+            ro[c] = ld4(a.rho[c] + 4 * i);
+        }
+        const float4 dz4 = ld4(a.dz + 4 * i);
+        const float xx = (float)(g.jb0 + (int)line) - g.cx;
+        float4 ow[3], og[3], oe = f4zero();
+#pragma unroll
+        for (int c = 0; c < 3; c++) { ow[c] = f4zero(); og[c] = f4zero(); }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!(tv[k] & T_MASK)) continue;
+            float Up[3][4], IIp[3], rho[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) Up[c][kk] = f4get(U[c][kk], k);
+                IIp[c] = f4get(II[c], k);
+                rho[c] = f4get(ro[c], k);
+            }
+            const float yy = (float)(g.ib0 + x + k) - g.cy;
+            float w[3], gg[3], e0;
+            depth_coeffs_px(lc, Up, IIp, rho, f4get(dz4, k), g.fx, g.fy, xx, yy, w, gg, e0);
+#pragma unroll
+            for (int c = 0; c < 3; c++) { f4set(ow[c], k, w[c]); f4set(og[c], k, gg[c]); }
+            f4set(oe, k, e0);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) { st4(a.w[c] + 4 * i, ow[c]); st4(a.gq[c] + 4 * i, og[c]); }
+        st4(a.e0 + 4 * i, oe);
+    }
+}
+
+}  // namespace srps
