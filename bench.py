@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- SRmeetsPS outer loop on B200 (BASELINE.json metric: ms per outer iteration).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload 4k|1080p|mitten-size]
+
+A *step* is one outer iteration (lighting -> albedo -> depth CG (101 passes) -> normals/energy,
+SRPS.cu:276-317) of the BASELINE.json workload: synthetic 4096x4096 HR scene, sf=4, 32 images
+(config 4), which fits one GPU.  Prints ONE JSON line.
+
+ value     device time per outer iteration, state resident in HBM (cudaEvents on the context's stream)
+ e2e       the same solve through the C ABI from pinned HOST buffers: upload + K iterations + download
+ roofline  the CG stencil kernel timed alone, algorithmic bytes / time vs MEASURED_PEAKS.json
+ cpu_baseline  oracle C/OpenMP transcription on a bounded sample (rank 0, N=1 only)
+
+--impl reference times the reference's own CUDA build (oracle/_ref/ref_replay: unmodified
+devicecalls.cu + legacy-cuSPARSE shim) on a bounded sample of the workload (it cannot run
+4096^2 x 32: int32 nnz overflow) and reports the per-pixel-linear extrapolation.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (h, w, sf, n, seed)        BASELINE.md §3
+    "4k": (4096, 4096, 4, 32, 2000),         # config 4 (the metric's configuration)
+    "1080p": (1080, 1920, 4, 20, 1000),      # config 3
+    "small": (512, 512, 4, 8, 7),            # CI-sized
+}
+METRIC = "ms per outer iteration (4096x4096 HR, sf=4, 32 images)"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(h, w, sf, n, seed, full_pixels):
+    """oracle port (C/OpenMP transcription of the same iteration) on a bounded sample."""
+    import numpy as np
+    from oracle import srps_oracle as o
+    from oracle.port import Port
+    sc = o.synth_scene(h, w, sf, n, seed=seed)
+    st = o.init_state(sc["I"], sc["z"], sc["z0s"], sc["ops"], sc["K"], np.float32)
+    pt = Port(sc["ops"], sc["n"], sc["c"], st["fx"], st["fy"], st["xx"], st["yy"])
+    stp = {k: np.ascontiguousarray(st[k]).copy() for k in ("s", "rho", "z", "N", "dz", "I", "z0s")}
+    pt.outer_iteration(stp)                       # warm-up (page faults, OpenMP pool)
+    t0 = time.perf_counter()
+    iters = 2
+    for _ in range(iters):
+        pt.outer_iteration(stp)
+    ms = (time.perf_counter() - t0) * 1e3 / iters
+    scale = full_pixels / float(h * w)
+    return {"value": ms * scale, "unit": "ms per outer iteration", "cores": pt.threads(), "kind": "port",
+            "sample": f"{h}x{w} sf={sf} n={n} full mask, {iters} outer iterations after 1 warm-up, reference-CG albedo, "
+                      f"measured {ms:.1f} ms/iter, scaled x{scale:g} (work is linear in pixels) to the {full_pixels}-pixel workload"}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own CUDA build (unmodified devicecalls.cu) on a bounded sample."""
+    if rank != 0:
+        return
+    h, w, sf, n, seed = WORKLOADS[args.workload]
+    full_pixels = h * w
+    replay = os.path.join(ROOT, "oracle", "_ref", "ref_replay")
+    line = {"impl": "reference", "metric": METRIC if args.workload == "4k" else f"ms per outer iteration ({args.workload})",
+            "unit": "ms", "higher_is_better": False, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "dtype": "f32", "data": "synthetic", "vs_baseline": None, "scaling": "strong"}
+    import numpy as np
+    from oracle import datasets as ds
+    from oracle import srps_oracle as o
+    from srmeetsps_cuda_b200.snapshot import write_snapshot
+    if os.path.exists(replay) and not args.ref_cpu:
+        sh, sw = args.ref_sample, args.ref_sample
+        sc = o.synth_scene(sh, sw, sf, n, seed=seed)
+        with tempfile.TemporaryDirectory() as td:
+            snap = os.path.join(td, "in.snap")
+            write_snapshot(snap, ds.replay_snapshot_arrays(sc))
+            res = subprocess.run([replay, snap, os.path.join(td, "o"), "--iters", str(args.steps + args.warmup), "--no-dump"],
+                                 capture_output=True, text=True)
+        rows = [json.loads(ln.replace(": nan", ": NaN")) for ln in res.stdout.splitlines() if ln.startswith('{"iteration"')]
+        if res.returncode == 0 and len(rows) >= args.steps + args.warmup:
+            ms = float(np.mean([r["ms_total"] for r in rows[args.warmup:]]))
+            scale = full_pixels / float(sh * sw)
+            line.update({"value": ms * scale, "ms_per_step": ms * scale,
+                         "config": {"workload": f"{h}x{w} sf={sf} n={n}", "sample": f"{sh}x{sw}", "scaled_by": scale},
+                         "cpu_baseline": {"value": ms * scale, "unit": "ms per outer iteration", "cores": 0, "kind": "reference",
+                                          "sample": f"reference CUDA build (cuSPARSE/cuBLAS path on the GPU, no CPU path exists) on "
+                                                    f"{sh}x{sw} sf={sf} n={n}: {ms:.1f} ms/iter measured, x{scale:g} per-pixel-linear "
+                                                    f"extrapolation; it cannot run {h}x{w}x{n} (int32 nnz overflow, SURVEY F7)"},
+                         "e2e": {"value": ms * scale, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                         "phases_ms_sample": {k: float(np.mean([r[k] for r in rows[args.warmup:]])) for k in
+                                              ("ms_lighting", "ms_albedo", "ms_depth", "ms_normals")}})
+            print(json.dumps(line))
+            return
+        sys.stderr.write(f"ref_replay failed (rc={res.returncode}); falling back to the CPU port\n{res.stderr[-2000:]}\n")
+    cb = cpu_baseline(args.cpu_sample, args.cpu_sample, sf, n, seed, full_pixels)
+    line.update({"value": cb["value"], "ms_per_step": cb["value"], "config": {"workload": f"{h}x{w} sf={sf} n={n}"},
+                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local):
+    import numpy as np
+    import torch
+    from srmeetsps_cuda_b200 import Context
+    from srmeetsps_cuda_b200.synth import synth_scene_torch
+
+    h, w, sf, n, seed = WORKLOADS[args.workload]
+    torch.cuda.set_device(local)
+    # N > 1: independent replicas, one scene per GPU (BASELINE config 5 pattern; the strip partition
+    # of one scene across GPUs is not implemented yet -- DESIGN.md §Multi-GPU)
+    sc = synth_scene_torch(h, w, sf, n, seed + rank, device=f"cuda:{local}")
+    npix = h * w
+    ctx = Context(sc["mask"], n, sf, sc["K"], device=local, albedo_mode=args.albedo)
+    ctx.upload_state(sc["I"], sc["z"], sc["z0s"])
+    torch.cuda.empty_cache()
+
+    # ---- device-resident timing: W warm-up + K timed outer iterations
+    for _ in range(args.warmup):
+        ctx.outer_iteration()
+    sampler = ClockSampler(local)
+    barrier(world)
+    sampler.start()
+    l0 = ctx.timings()["launches"]
+    per = []
+    phases = {"ms_lighting": [], "ms_albedo": [], "ms_depth": [], "ms_normals": [], "ms_depth_cg": []}
+    cg_iters = []
+    energies = []
+    for _ in range(args.steps):
+        e, k = ctx.outer_iteration()
+        t = ctx.timings()
+        per.append(t["ms_total"])
+        for key in phases:
+            phases[key].append(t[key])
+        cg_iters.append(k)
+        energies.append(e)
+    launches = ctx.timings()["launches"] - l0
+    barrier(world)
+    clocks = sampler.stop()
+    ms_step = max_over_ranks(float(np.mean(per)), world)
+
+    # ---- end to end through the C ABI from pinned host memory: upload + K iterations + download
+    out = {k: torch.empty(s, dtype=torch.float32, pin_memory=True).numpy() for k, s in
+           (("z", (npix,)), ("rho", (3, npix)), ("N", (4, npix)), ("s", (n, 3, 4)))}
+    barrier(world)
+    ctx.timer_start()
+    ctx.upload_state(sc["I"], sc["z"], sc["z0s"])
+    e2e_energies = ctx.run(fixed_iters=args.steps)
+    for k in out:
+        ctx.download(k, out=out[k])
+    e2e_ms_total = ctx.timer_stop()
+    e2e_ms = max_over_ranks(e2e_ms_total / args.steps, world)
+    h2d = (sc["I"].nbytes + sc["z"].nbytes + sc["z0s"].nbytes) / args.steps
+    d2h = sum(v.nbytes for v in out.values()) / args.steps + 16
+
+    # ---- roofline of the dominant kernel (CG stencil), timed alone
+    prof = ctx.profile_kernels(reps=30)
+    peak, peak_src = measured_peaks()
+    alg_bytes = 28.0 * npix          # reads r, p, w0..2 ; writes p, y  
+    achieved = alg_bytes / (prof["cg_stencil"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "stencil_kernel<MODE_ITER>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": prof["cg_stencil"],
+                "other_kernels": {
+                    "cg_update_kernel": {"ms": prof["cg_update"], "GBps": 24.0 * npix / (prof["cg_update"] * 1e-3) / 1e9},
+                    "lighting_pass": {"ms": prof["lighting_pass"], "GBps": (4.0 * n * 3 + 24) * npix / (prof["lighting_pass"] * 1e-3) / 1e9},
+                    "project_pass": {"ms": prof["project_pass"], "GBps": (4.0 * n * 3 + 72) * npix / (prof["project_pass"] * 1e-3) / 1e9}},
+                "cg_loop_GBps_survey_64B": 64.0 * npix * float(np.mean(cg_iters)) / (float(np.mean(phases["ms_depth_cg"])) * 1e-3) / 1e9,
+                "cg_loop_GBps_actual_52B": 52.0 * npix * float(np.mean(cg_iters)) / (float(np.mean(phases["ms_depth_cg"])) * 1e-3) / 1e9}
+    ctx.close()
+
+    if rank != 0:
+        return
+    cb = None
+    if world == 1 and not args.no_cpu:
+        cb = cpu_baseline(args.cpu_sample, args.cpu_sample, sf, n, seed, npix)
+    line = {
+        "metric": METRIC if args.workload == "4k" else f"ms per outer iteration ({args.workload})",
+        "value": ms_step / world, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": False,
+        "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{h}x{w} HR, sf={sf}, {n} images, full mask (BASELINE config {'4' if args.workload == '4k' else '3'})",
+                   "albedo": args.albedo, "depth_cg": "reference schedule: un-preconditioned, 101 passes",
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas, one scene per GPU (value = ms per scene-iteration)",
+                   "l2": f"image stack {sc['I'].nbytes / 1e9:.2f} GB and CG working set {28 * npix / 1e6:.0f} MB per pass exceed the 126 MB L2: no flush needed"},
+        "e2e": {"value": e2e_ms / world, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "what": f"srps_upload_state (pinned host) + {args.steps} outer iterations + download of z, rho, N, s; total {e2e_ms_total:.1f} ms / {args.steps}"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cb,
+        "phases_ms": {k: float(np.mean(v)) for k, v in phases.items()},
+        "cg_iters_per_s": float(np.mean(cg_iters)) / (float(np.mean(phases["ms_depth_cg"])) * 1e-3),
+        "cg_iters": int(np.mean(cg_iters)),
+        "energy_last": float(energies[-1]),
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="4k", choices=list(WORKLOADS))
+    ap.add_argument("--albedo", default="closed_form", choices=["closed_form", "reference_cg"])
+    ap.add_argument("--cpu-sample", type=int, default=2048, help="edge of the square sample the CPU port is timed on")
+    ap.add_argument("--ref-sample", type=int, default=1024, help="edge of the square sample the reference CUDA build is timed on")
+    ap.add_argument("--ref-cpu", action="store_true", help="reference arm: use the CPU port instead of the reference CUDA build")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank, world, local = dist_setup(args.gpus)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

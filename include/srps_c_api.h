@@ -43,6 +43,11 @@ extern "C" {
 #define SRPS_BUF_N    3   /* [4][npix]    */
 #define SRPS_BUF_DZ   4   /* [npix]       */
 #define SRPS_BUF_Z0S  5   /* [npixs]      */
+/* read-only internals (srps_download only; tests): per-pixel depth coefficients and CG residual */
+#define SRPS_BUF_W    16  /* [3][npix]  (rho_c/dz)^2                          */
+#define SRPS_BUF_G    17  /* [3][npix]  g = sum t B      (devicecalls.cu:744) */
+#define SRPS_BUF_E0   18  /* [npix]     sum B^2                                */
+#define SRPS_BUF_R    19  /* [npix]     CG residual plane                      */
 
 typedef struct srps_ctx srps_ctx;
 
@@ -103,6 +108,18 @@ int  srps_run(srps_ctx* ctx, int max_outer, float tol, int fixed_iters, float* e
 
 int  srps_get_timings(const srps_ctx* ctx, srps_timings* out);
 int  srps_synchronize(srps_ctx* ctx);
+
+/* Device-side stopwatch on the context's stream (cudaEvent): everything the context enqueues
+ * between start and stop -- uploads, kernels, downloads -- is inside the measured interval. */
+int  srps_timer_start(srps_ctx* ctx);
+int  srps_timer_stop(srps_ctx* ctx, float* ms);
+
+/* Measurement hook (bench.py roofline): average device time (ms, cudaEvent on the launching
+ * stream) of `reps` back-to-back launches of one kernel alone.  out_ms[0] = CG stencil kernel
+ * (p <- r + beta p; y <- A p; p.y), [1] = CG update kernel, [2] = lighting stack pass,
+ * [3] = stack-projection pass (+ fused albedo / depth coefficients).  Needs one completed
+ * srps_outer_iteration; leaves the loop state UNDEFINED (re-upload before further use). */
+int  srps_profile_kernels(srps_ctx* ctx, int reps, float* out_ms);
 
 /* Test hook: y = (Kt K + G^T M G) p with the M of the current rho/dz/s (masked host vectors). */
 int  srps_apply_depth_operator(srps_ctx* ctx, const float* p_host, float* y_host);

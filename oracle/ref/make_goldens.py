@@ -28,6 +28,7 @@ SCENES = {
     # name: (builder, iterations, subsample stride for rho/N)
     "synth_ellipse": (lambda: o.synth_scene(96, 128, 2, 6, seed=7, mask_kind="ellipse"), 3, 1),
     "synth_random": (lambda: o.synth_scene(64, 96, 4, 5, seed=11, mask_kind="random"), 3, 1),
+    "synth_random95": (lambda: o.synth_scene(64, 96, 2, 6, seed=12, mask_kind="random95"), 3, 1),
     "synth_full": (lambda: o.synth_scene(64, 64, 4, 8, seed=3, mask_kind="full"), 3, 1),
     "mitten": (lambda: ds.scene_from_snapshot(np.load(os.path.join(ROOT, "tests", "golden", "mitten_init.npz"))), 3, 4),
 }
@@ -44,7 +45,7 @@ def run_scene(name, outdir):
         sys.stderr.write(res.stderr)
         if res.returncode != 0:
             raise RuntimeError(f"ref_replay failed on {name}: rc={res.returncode}\n{res.stdout}\n{res.stderr}")
-        log = [json.loads(ln) for ln in res.stdout.splitlines() if ln.startswith("{")]
+        log = [json.loads(ln.replace(": nan", ": NaN").replace(": -nan", ": NaN")) for ln in res.stdout.splitlines() if ln.startswith("{")]
         out = {"stride": np.int32(stride), "iters": np.int32(iters)}
         for it in range(1, iters + 1):
             d = read_snapshot(f"{prefix}_it{it:02d}.snap")

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libsrps_b200.so")
 SRPS_ALBEDO_CLOSED_FORM = 0
 SRPS_ALBEDO_REFERENCE_CG = 1
 BUF_S, BUF_RHO, BUF_Z, BUF_N, BUF_DZ, BUF_Z0S = range(6)
+BUF_W, BUF_G, BUF_E0, BUF_R = 16, 17, 18, 19
 
 
 class Problem(C.Structure):
@@ -44,6 +45,9 @@ EXPORTS = {
     "srps_run": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "srps_get_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "srps_synchronize": (C.c_int, [C.c_void_p]),
+    "srps_timer_start": (C.c_int, [C.c_void_p]),
+    "srps_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "srps_profile_kernels": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "srps_apply_depth_operator": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "srps_build_info": (C.c_char_p, []),
 }

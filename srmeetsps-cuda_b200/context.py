@@ -82,8 +82,11 @@ class Context:
         self._ck(self.lib.srps_upload_images_u8(self._ctx, _ptr(I8)), "srps_upload_images_u8")
 
     _SHAPES = {L.BUF_S: lambda s: (s.n, s.c, 4), L.BUF_RHO: lambda s: (s.c, s.npix), L.BUF_Z: lambda s: (s.npix,),
-               L.BUF_N: lambda s: (4, s.npix), L.BUF_DZ: lambda s: (s.npix,), L.BUF_Z0S: lambda s: (s.npixs,)}
-    _NAMES = {"s": L.BUF_S, "rho": L.BUF_RHO, "z": L.BUF_Z, "N": L.BUF_N, "dz": L.BUF_DZ, "z0s": L.BUF_Z0S}
+               L.BUF_N: lambda s: (4, s.npix), L.BUF_DZ: lambda s: (s.npix,), L.BUF_Z0S: lambda s: (s.npixs,),
+               L.BUF_W: lambda s: (3, s.npix), L.BUF_G: lambda s: (3, s.npix), L.BUF_E0: lambda s: (s.npix,),
+               L.BUF_R: lambda s: (s.npix,)}
+    _NAMES = {"s": L.BUF_S, "rho": L.BUF_RHO, "z": L.BUF_Z, "N": L.BUF_N, "dz": L.BUF_DZ, "z0s": L.BUF_Z0S,
+              "w": L.BUF_W, "g": L.BUF_G, "e0": L.BUF_E0, "r": L.BUF_R}
 
     def download(self, name, out=None):
         which = self._NAMES[name]
@@ -139,6 +142,20 @@ class Context:
 
     def synchronize(self):
         self._ck(self.lib.srps_synchronize(self._ctx), "srps_synchronize")
+
+    def timer_start(self):
+        self._ck(self.lib.srps_timer_start(self._ctx), "srps_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._ck(self.lib.srps_timer_stop(self._ctx, C.byref(ms)), "srps_timer_stop")
+        return float(ms.value)
+
+    def profile_kernels(self, reps=20):
+        """Average device ms of the dominant kernels timed alone (state is undefined afterwards)."""
+        out = (C.c_float * 4)()
+        self._ck(self.lib.srps_profile_kernels(self._ctx, int(reps), out), "srps_profile_kernels")
+        return dict(cg_stencil=out[0], cg_update=out[1], lighting_pass=out[2], project_pass=out[3])
 
     def apply_depth_operator(self, p):
         p = np.ascontiguousarray(p, dtype=np.float32)

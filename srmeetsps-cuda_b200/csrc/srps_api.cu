@@ -44,7 +44,7 @@ struct srps_ctx {
     unsigned char* lrmask = nullptr;
     int* idx = nullptr; int* idx_lr = nullptr;
     float* I = nullptr; float* I_base = nullptr;
-    float *z = nullptr, *r = nullptr, *p = nullptr, *y = nullptr, *e0 = nullptr, *dz = nullptr, *dz_new = nullptr;
+    float *z = nullptr, *r = nullptr, *p = nullptr, *p2 = nullptr, *y = nullptr, *e0 = nullptr, *dz = nullptr, *dz_new = nullptr;
     float *w[3]{}, *gq[3]{}, *N[3]{}, *N_new[3]{}, *rho[3]{};
     float *U = nullptr, *ad[3]{}, *ar[3]{}, *ap[3]{};    // reference-CG albedo only
     float* z0lr = nullptr;
@@ -193,7 +193,8 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         auto next = [&]() { return ctx->plane_base + (k++) * g.plane + g.origin(); };
         ctx->z = next(); ctx->r = next(); ctx->p = next(); ctx->y = next(); ctx->e0 = next(); ctx->dz = next(); ctx->dz_new = next();
         for (int c = 0; c < 3; c++) { ctx->w[c] = next(); ctx->gq[c] = next(); ctx->N[c] = next(); ctx->N_new[c] = next(); ctx->rho[c] = next(); }
-        k += 3;   // spare
+        ctx->p2 = next();
+        k += 2;   // spare
         if (refcg) for (int c = 0; c < 3; c++) { ctx->ad[c] = next(); ctx->ar[c] = next(); ctx->ap[c] = next(); }
     }
     if (refcg) {
@@ -447,6 +448,10 @@ extern "C" int srps_download(srps_ctx* ctx, int which, float* host) {
             if (!rc) { CK(cudaStreamSynchronize(ctx->stream)); for (int p = 0; p < ctx->npix; p++) host[(size_t)3 * ctx->npix + p] = 1.f; }   // devicecalls.cu:175
             break;
         case SRPS_BUF_DZ: rc = gather_to_host(ctx, ctx->dz, host); break;
+        case SRPS_BUF_W: for (int c = 0; c < 3 && !rc; c++) rc = gather_to_host(ctx, ctx->w[c], host + (size_t)c * ctx->npix); break;
+        case SRPS_BUF_G: for (int c = 0; c < 3 && !rc; c++) rc = gather_to_host(ctx, ctx->gq[c], host + (size_t)c * ctx->npix); break;
+        case SRPS_BUF_E0: rc = gather_to_host(ctx, ctx->e0, host); break;
+        case SRPS_BUF_R: rc = gather_to_host(ctx, ctx->r, host); break;
         case SRPS_BUF_Z0S:
             LAUNCH(ctx, gather_kernel, (ctx->npixs + 255) / 256, 256, (const float*)ctx->z0lr, ctx->idx_lr, (float*)ctx->staging, ctx->npixs);
             CK(cudaGetLastError());
@@ -529,8 +534,12 @@ extern "C" int srps_albedo(srps_ctx* ctx) {
     return 0;
 }
 
-static int launch_cg_iterations(srps_ctx* ctx, const StencilArgs& sa, const UpdateArgs& ua, int passes) {
+static int launch_cg_iterations(srps_ctx* ctx, StencilArgs sa, UpdateArgs ua, int passes) {
     for (int k = 0; k < passes; k++) {
+        // ping-pong the search direction: pass k reads p[k&1] (tile + halo) and writes p[(k+1)&1]
+        sa.p_in = (k & 1) ? ctx->p2 : ctx->p;
+        sa.p_out = (k & 1) ? ctx->p : ctx->p2;
+        ua.p = sa.p_out;
         LAUNCH(ctx, stencil_kernel<MODE_ITER>, ctx->grid_stencil, CG_NT, sa);
         LAUNCH(ctx, cg_update_kernel, ctx->grid_update, CG_NT, ua);
     }
@@ -539,7 +548,7 @@ static int launch_cg_iterations(srps_ctx* ctx, const StencilArgs& sa, const Upda
 
 static void fill_stencil_args(srps_ctx* ctx, StencilArgs& sa) {
     sa.g = ctx->g; sa.types = ctx->types; sa.w0 = ctx->w[0]; sa.w1 = ctx->w[1]; sa.w2 = ctx->w[2]; sa.lc = ctx->lc;
-    sa.vin = ctx->z; sa.r = ctx->r; sa.p = ctx->p; sa.y = ctx->y; sa.g0 = ctx->gq[0]; sa.g1 = ctx->gq[1]; sa.g2 = ctx->gq[2];
+    sa.vin = ctx->z; sa.r = ctx->r; sa.p_in = ctx->p; sa.p_out = ctx->p2; sa.y = ctx->y; sa.g0 = ctx->gq[0]; sa.g1 = ctx->gq[1]; sa.g2 = ctx->gq[2];
     sa.z0lr = ctx->z0lr; sa.sc = ctx->sc; sa.partials = ctx->partials; sa.ticket = ctx->tickets + 4;
     sa.tiles_x = ctx->tiles_x; sa.tiles_y = ctx->tiles_y;
 }
@@ -690,4 +699,104 @@ extern "C" int srps_apply_depth_operator(srps_ctx* ctx, const float* p_host, flo
     LAUNCH(ctx, stencil_kernel<MODE_APPLY>, ctx->grid_stencil, CG_NT, sa);
     CK(cudaGetLastError());
     return gather_to_host(ctx, ctx->y, y_host);
+}
+
+extern "C" int srps_timer_start(srps_ctx* ctx) {
+    if (!ctx) return SRPS_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+    return 0;
+}
+
+extern "C" int srps_timer_stop(srps_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return SRPS_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    cudaEvent_t e1;
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(ms, ctx->ev[7], e1));
+    CK(cudaEventDestroy(e1));
+    return 0;
+}
+
+extern "C" int srps_profile_kernels(srps_ctx* ctx, int reps, float* out_ms) {
+    if (!ctx || !out_ms || reps < 1) return fail(ctx, SRPS_E_INVALID, "bad argument");
+    if (!ctx->have_state || !ctx->coeffs_valid) return fail(ctx, SRPS_E_STATE, "run one srps_outer_iteration first");
+    CK(cudaSetDevice(ctx->device));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    // keep the CG kernels active for the whole measurement with fixed, benign scalars
+    CgScalars sc = ctx->h_sc[0];
+    sc.active = 1; sc.beta = 0.5f; sc.alpha = 1e-3f; sc.r1 = 1.0; sc.r0 = 1.0; sc.k = 0; sc.max_iter = 1 << 30; sc.tol2 = 0.f;
+    CgScalars* h = ctx->h_sc;
+    const CgScalars saved = h[0];
+    h[0] = sc;
+    CK(cudaMemcpyAsync(ctx->sc, h, sizeof(CgScalars), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    StencilArgs sa{};
+    fill_stencil_args(ctx, sa);
+    UpdateArgs ua{};
+    ua.x = ctx->y; ua.r = ctx->r; ua.p = ctx->p; ua.y = ctx->p2; ua.n4 = ctx->n4; ua.sc = ctx->sc; ua.partials = ctx->partials;
+    ua.ticket = ctx->tickets + 5;
+    // warm-up + stencil alone
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) CK(cudaEventRecord(e0, ctx->stream));
+        for (int k = 0; k < (pass ? reps : 2); k++) {
+            sa.p_in = (k & 1) ? ctx->p2 : ctx->p;
+            sa.p_out = (k & 1) ? ctx->p : ctx->p2;
+            LAUNCH(ctx, stencil_kernel<MODE_ITER>, ctx->grid_stencil, CG_NT, sa);
+        }
+    }
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&out_ms[0], e0, e1));
+    out_ms[0] /= reps;
+    CK(cudaMemcpyAsync(h + 3, ctx->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int still_active = h[3].active;
+    // update kernel alone (the stencil's last block rewrote alpha: reset the scalars)
+    CK(cudaMemcpyAsync(ctx->sc, h, sizeof(CgScalars), cudaMemcpyHostToDevice, ctx->stream));
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) CK(cudaEventRecord(e0, ctx->stream));
+        for (int k = 0; k < (pass ? reps : 2); k++) LAUNCH(ctx, cg_update_kernel, ctx->grid_update, CG_NT, ua);
+    }
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&out_ms[1], e0, e1));
+    out_ms[1] /= reps;
+    // restore the reference CG parameters
+    h[0] = saved;
+    CK(cudaMemcpyAsync(ctx->sc, h, sizeof(CgScalars), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // the two stack passes (each is one launch of the dominant kernel of its phase)
+    const int sreps = reps < 3 ? reps : 3;
+    int rc;
+    if ((rc = srps_lighting(ctx))) return rc;        // warm-up
+    CK(cudaEventRecord(e0, ctx->stream));
+    for (int k = 0; k < sreps; k++) if ((rc = srps_lighting(ctx))) return rc;
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&out_ms[2], e0, e1));
+    out_ms[2] /= sreps;
+    const int mode = ctx->prob.albedo_mode;
+    ctx->prob.albedo_mode = SRPS_ALBEDO_CLOSED_FORM;
+    rc = srps_albedo(ctx);
+    if (!rc) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        for (int k = 0; k < sreps && !rc; k++) rc = srps_albedo(ctx);
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&out_ms[3], e0, e1));
+        out_ms[3] /= sreps;
+    }
+    ctx->prob.albedo_mode = mode;
+    CK(cudaEventDestroy(e0));
+    CK(cudaEventDestroy(e1));
+    ctx->have_state = false;
+    ctx->coeffs_valid = false;
+    if (rc) return rc;
+    if (!still_active) return fail(ctx, SRPS_E_STATE, "profile: CG scalars went non-finite, stencil timing invalid");
+    return 0;
 }

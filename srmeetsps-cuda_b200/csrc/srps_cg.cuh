@@ -33,7 +33,9 @@ struct StencilArgs {
     // MODE_APPLY: y <- A vin (test hook)
     const float* vin;             // z (INIT) / p (APPLY)
     const float* r;               // ITER: residual (read)
-    float* p;                     // ITER: search direction (read + write)
+    const float* p_in;            // ITER: previous search direction (read, tile + halo)
+    float* p_out;                 // ITER: new search direction (written to the OTHER plane: neighbouring
+                                  //       tiles recompute p on their halo from p_in, so it must stay intact)
     float* y;                     // output
     const float* g0; const float* g1; const float* g2;   // INIT: G^T g right-hand side planes
     const float* z0lr;            // INIT: dense LR depth
@@ -84,10 +86,10 @@ __global__ void __launch_bounds__(CG_NT, 3) stencil_kernel(const StencilArgs a) 
             if (ok) {
                 t = *reinterpret_cast<const uchar4*>(a.types + off);
                 if (MODE == MODE_ITER) {
-                    const float4 r4 = ld4(a.r + off), p4 = ld4(a.p + off);
+                    const float4 r4 = ld4(a.r + off), p4 = ld4(a.p_in + off);
                     v.x = r4.x + beta * p4.x; v.y = r4.y + beta * p4.y;
                     v.z = r4.z + beta * p4.z; v.w = r4.w + beta * p4.w;
-                    if (ly >= 1 && ly <= TY && q >= 1 && q <= TX / 4 && j < ny) st4(a.p + off, v);
+                    if (ly >= 1 && ly <= TY && q >= 1 && q <= TX / 4 && j < ny) st4(a.p_out + off, v);
                 } else {
                     v = ld4(a.vin + off);
                 }

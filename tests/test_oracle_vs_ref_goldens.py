@@ -1,0 +1,55 @@
+"""Pins the oracle: the CPU restatements (numpy fp32/fp64 and the C transcription) against the
+outputs of the reference's own UNMODIFIED device code (oracle/_ref/ref_replay on a B200,
+fixtures tests/golden/ref_*.npz made by oracle/ref/make_goldens.py), after every outer iteration."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, rel_rmse
+from oracle import srps_oracle as o
+from oracle.port import Port
+from oracle.ref.make_goldens import SCENES
+
+
+@pytest.mark.parametrize("name", ["synth_ellipse", "synth_random", "synth_random95", "synth_full", "mitten"])
+def test_c_port_matches_reference_cuda(name):
+    path = os.path.join(GOLDEN, f"ref_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip("reference goldens not generated: parity unpinned")
+    g = np.load(path)
+    sc = SCENES[name][0]()
+    stride = int(g["stride"])
+    st = o.init_state(sc["I"], sc["z"], sc["z0s"], sc["ops"], sc["K"], np.float32)
+    pt = Port(sc["ops"], sc["n"], sc["c"], st["fx"], st["fy"], st["xx"], st["yy"])
+    stp = {k: np.ascontiguousarray(st[k]).copy() for k in ("s", "rho", "z", "N", "dz", "I", "z0s")}
+    for it in range(1, int(g["iters"]) + 1):
+        e, k, ak = pt.outer_iteration(stp)
+        e_ref = float(g[f"energy_{it}"][0])
+        assert k == 101
+        assert rel_rmse(stp["z"], g[f"z_{it}"]) <= 1e-4, it
+        assert np.abs(stp["rho"][:, ::stride] - g[f"rho_{it}"]).max() <= 1e-3, it
+        assert np.abs(stp["s"] - g[f"s_{it}"]).max() <= 5e-3, it
+        # normals amplify depth noise by fx/z per pixel difference; synth_random is barely constrained (9 LR samples)
+        assert np.abs(stp["N"][:, ::stride] - g[f"N_{it}"]).max() <= (3e-2 if name == "synth_random" else 5e-3), it
+        assert abs(e - e_ref) <= 1e-3 * abs(e_ref), (it, e, e_ref)
+
+
+@pytest.mark.parametrize("name", ["synth_random", "synth_random95", "synth_full"])
+def test_numpy_oracle_matches_reference_cuda(name):
+    """The literal (assembled sparse system) restatement, fp32, small scenes."""
+    path = os.path.join(GOLDEN, f"ref_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip("reference goldens not generated: parity unpinned")
+    g = np.load(path)
+    sc = SCENES[name][0]()
+    st = o.init_state(sc["I"], sc["z"], sc["z0s"], sc["ops"], sc["K"], np.float32)
+    for it in range(1, int(g["iters"]) + 1):
+        e, k, ak = o.outer_iteration(st, sc["ops"], np.float32, assembled=True)
+        e_ref = float(g[f"energy_{it}"][0])
+        assert k == 101
+        assert rel_rmse(st["z"], g[f"z_{it}"]) <= 1e-4, it
+        # synth_random has 9 LR depth samples for 3602 pixels: the 101-pass CG is far from converged and
+        # fp32 summation-order noise (numpy vs cuSPARSE) shows up in the next albedo at the 2e-3 level
+        assert np.abs(st["rho"] - g[f"rho_{it}"]).max() <= (5e-3 if name == "synth_random" else 1e-3), it
+        assert abs(e - e_ref) <= 1e-3 * abs(e_ref), (it, e, e_ref)
