@@ -59,6 +59,7 @@ struct srps_ctx {
     // launch geometry
     int grid_stencil = 0, grid_update = 0, grid_stack = 0, grid_light_x = 0, light_groups = 0, grid_ep = 0, grid_al = 0, grid_gram = 0;
     int tiles_x = 0, tiles_y = 0;
+    int use_strip = 0, strip_n = 0, strip_chunks = 0, strip_cl = 0, grid_strip = 0;
     long long n4 = 0;
     cudaGraphExec_t cg_graph = nullptr;
     int use_graph = 1;
@@ -242,6 +243,20 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stencil_kernel<MODE_ITER>, CG_NT, 0));
     ctx->grid_stencil = std::min(ctx->tiles_x * ctx->tiles_y, ctx->sm_count * std::max(1, occ));
+    {   // warp-strip operator (sf <= 4): strips of 30 float4 columns x chunks of lines, one warp each
+        const char* si = getenv("SRPS_STENCIL");
+        ctx->use_strip = (sf <= 4) && !(si && strcmp(si, "tile") == 0);
+        const int nq = (g.nx + 3) / 4;
+        ctx->strip_n = (nq + SW_COLS - 1) / SW_COLS;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stencil_strip_kernel<MODE_ITER, 4>, SW_NT, 0));
+        const int warps = ctx->sm_count * std::max(1, occ) * (SW_NT / 32);
+        int cl = (int)(((long long)g.ny * ctx->strip_n + warps - 1) / warps);
+        cl = std::min(256, std::max(8, round_up(cl, SW_G)));
+        ctx->strip_cl = cl;
+        ctx->strip_chunks = (g.ny + cl - 1) / cl;
+        const int nitems = ctx->strip_n * ctx->strip_chunks;
+        ctx->grid_strip = std::min((nitems + SW_NT / 32 - 1) / (SW_NT / 32), ctx->sm_count * std::max(1, occ));
+    }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_update_kernel, CG_NT, 0));
     ctx->grid_update = (int)std::min<long long>((ctx->n4 + CG_NT - 1) / CG_NT, (long long)ctx->sm_count * std::max(1, occ));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stack_project_kernel<true>, ST_NT, 0));
@@ -255,7 +270,7 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, normals_energy_kernel<true>, EP_NT, 0));
     ctx->grid_ep = (int)std::min<long long>((ctx->n4 + EP_NT - 1) / EP_NT, (long long)ctx->sm_count * std::max(1, occ));
     ctx->grid_al = (int)std::min<long long>((ctx->n4 + AL_NT - 1) / AL_NT, (long long)ctx->sm_count * 4);
-    long long pl = std::max<long long>({(long long)ctx->grid_stencil, (long long)ctx->grid_update, (long long)ctx->grid_ep,
+    long long pl = std::max<long long>({(long long)ctx->grid_stencil, (long long)ctx->grid_strip, (long long)ctx->grid_update, (long long)ctx->grid_ep,
                                         3ll * ctx->grid_al, 30ll * ctx->grid_gram,
                                         (long long)LIGHT_IB * 12 * ctx->grid_light_x * ctx->light_groups}) + 64;
     ctx->partials_len = pl;
@@ -534,23 +549,38 @@ extern "C" int srps_albedo(srps_ctx* ctx) {
     return 0;
 }
 
+static void fill_stencil_args(srps_ctx* ctx, StencilArgs& sa) {
+    sa.g = ctx->g; sa.types = ctx->types; sa.w0 = ctx->w[0]; sa.w1 = ctx->w[1]; sa.w2 = ctx->w[2]; sa.lc = ctx->lc;
+    sa.vin = ctx->z; sa.r = ctx->r; sa.p_in = ctx->p; sa.p_out = ctx->p2; sa.y = ctx->y; sa.g0 = ctx->gq[0]; sa.g1 = ctx->gq[1]; sa.g2 = ctx->gq[2];
+    sa.z0lr = ctx->z0lr; sa.sc = ctx->sc; sa.partials = ctx->partials; sa.ticket = ctx->tickets + 4;
+    sa.tiles_x = ctx->tiles_x; sa.tiles_y = ctx->tiles_y;
+    sa.strip_n = ctx->strip_n; sa.strip_chunks = ctx->strip_chunks; sa.strip_cl = ctx->strip_cl;
+}
+
+// y = A p (MODE_ITER: with the fused p-update and p.y) through the kernel variant of this context
+template <int MODE>
+static void launch_operator(srps_ctx* ctx, const StencilArgs& sa) {
+    if (ctx->use_strip) {
+        switch (ctx->g.sf) {
+            case 1: LAUNCH(ctx, (stencil_strip_kernel<MODE, 1>), ctx->grid_strip, SW_NT, sa); break;
+            case 2: LAUNCH(ctx, (stencil_strip_kernel<MODE, 2>), ctx->grid_strip, SW_NT, sa); break;
+            default: LAUNCH(ctx, (stencil_strip_kernel<MODE, 4>), ctx->grid_strip, SW_NT, sa); break;
+        }
+    } else {
+        LAUNCH(ctx, stencil_kernel<MODE>, ctx->grid_stencil, CG_NT, sa);
+    }
+}
+
 static int launch_cg_iterations(srps_ctx* ctx, StencilArgs sa, UpdateArgs ua, int passes) {
     for (int k = 0; k < passes; k++) {
         // ping-pong the search direction: pass k reads p[k&1] (tile + halo) and writes p[(k+1)&1]
         sa.p_in = (k & 1) ? ctx->p2 : ctx->p;
         sa.p_out = (k & 1) ? ctx->p : ctx->p2;
         ua.p = sa.p_out;
-        LAUNCH(ctx, stencil_kernel<MODE_ITER>, ctx->grid_stencil, CG_NT, sa);
+        launch_operator<MODE_ITER>(ctx, sa);
         LAUNCH(ctx, cg_update_kernel, ctx->grid_update, CG_NT, ua);
     }
     return 0;
-}
-
-static void fill_stencil_args(srps_ctx* ctx, StencilArgs& sa) {
-    sa.g = ctx->g; sa.types = ctx->types; sa.w0 = ctx->w[0]; sa.w1 = ctx->w[1]; sa.w2 = ctx->w[2]; sa.lc = ctx->lc;
-    sa.vin = ctx->z; sa.r = ctx->r; sa.p_in = ctx->p; sa.p_out = ctx->p2; sa.y = ctx->y; sa.g0 = ctx->gq[0]; sa.g1 = ctx->gq[1]; sa.g2 = ctx->gq[2];
-    sa.z0lr = ctx->z0lr; sa.sc = ctx->sc; sa.partials = ctx->partials; sa.ticket = ctx->tickets + 4;
-    sa.tiles_x = ctx->tiles_x; sa.tiles_y = ctx->tiles_y;
 }
 
 extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
@@ -696,7 +726,7 @@ extern "C" int srps_apply_depth_operator(srps_ctx* ctx, const float* p_host, flo
     StencilArgs sa{};
     fill_stencil_args(ctx, sa);
     sa.vin = ctx->p;
-    LAUNCH(ctx, stencil_kernel<MODE_APPLY>, ctx->grid_stencil, CG_NT, sa);
+    launch_operator<MODE_APPLY>(ctx, sa);
     CK(cudaGetLastError());
     return gather_to_host(ctx, ctx->y, y_host);
 }
@@ -746,7 +776,7 @@ extern "C" int srps_profile_kernels(srps_ctx* ctx, int reps, float* out_ms) {
         for (int k = 0; k < (pass ? reps : 2); k++) {
             sa.p_in = (k & 1) ? ctx->p2 : ctx->p;
             sa.p_out = (k & 1) ? ctx->p : ctx->p2;
-            LAUNCH(ctx, stencil_kernel<MODE_ITER>, ctx->grid_stencil, CG_NT, sa);
+            launch_operator<MODE_ITER>(ctx, sa);
         }
     }
     CK(cudaEventRecord(e1, ctx->stream));

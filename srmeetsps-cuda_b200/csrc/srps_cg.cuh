@@ -43,6 +43,7 @@ struct StencilArgs {
     double* partials;
     unsigned* ticket;
     int tiles_x, tiles_y;
+    int strip_n, strip_chunks, strip_cl;   // warp-strip kernel: strips per line, chunks per strip, lines per chunk
 };
 
 struct StencilSmem {
@@ -284,6 +285,185 @@ __global__ void __launch_bounds__(CG_NT, 3) stencil_kernel(const StencilArgs a) 
                 s->dot = total;
                 s->alpha = (float)s->r1 / (float)total;
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-strip variant of the operator (sf = 1, 2, 4; MODE_ITER / MODE_APPLY).
+//
+// One warp owns a strip of 30 float4 columns (+1 halo float4 column on each side, lanes 0 and 31)
+// and marches down a chunk of lines in groups of 4, holding a 6-line register window of the search
+// direction.  No shared memory, no block barriers: horizontal neighbours travel by warp shuffle,
+// the line above hands its forward x-row contribution down in registers, backward rows (mask
+// borders only) are evaluated under a warp vote.  Every global access is a full 512-byte warp
+// request; the only redundancy is the two halo lanes (6.7 % more L2->SM traffic, no extra DRAM
+// traffic) and one prologue line per chunk.
+// ---------------------------------------------------------------------------------------------
+constexpr int SW_NT = 128;       // 4 independent warps per CTA
+constexpr int SW_COLS = 30;      // output float4 columns per warp
+constexpr int SW_G = 4;          // lines per group (multiple of sf)
+
+struct LineQ { float4 q0f, q0b, q1f, q1b, own; };
+
+__device__ __forceinline__ unsigned ld_types(const unsigned char* t, long long off) {
+    return *reinterpret_cast<const unsigned*>(t + off);
+}
+
+// q = M (G p) for the 4 pixels of one float4 of a line; returns the pieces the gather needs:
+// q0f/q0b: x-row value where the pixel's x-row is forward / backward, q1f/q1b likewise for y,
+// own = q2 - (own x-row) - (own y-row).
+__device__ __forceinline__ LineQ line_q(const LightConsts& lc, float fx, float fy, float xx, float yy0, unsigned t4,
+                                        const float4& pc, const float4& up, const float4& dn, float left, float right,
+                                        const float4& w0, const float4& w1, const float4& w2) {
+    LineQ o;
+    const float pcv[6] = {left, pc.x, pc.y, pc.z, pc.w, right};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const unsigned t = (t4 >> (8 * k)) & 0xffu;
+        const float c = pcv[k + 1];
+        const float dxp = (t & T_XF) ? f4get(dn, k) - c : ((t & T_XB) ? c - f4get(up, k) : 0.f);
+        const float dyp = (t & T_YF) ? pcv[k + 2] - c : ((t & T_YB) ? c - pcv[k] : 0.f);
+        const Qm m = make_qm(lc, f4get(w0, k), f4get(w1, k), f4get(w2, k));
+        float q0, q1, q2;
+        apply_m(m, fx, fy, xx, yy0 + (float)k, dxp, dyp, c, q0, q1, q2);
+        const float a0 = (t & T_XF) ? q0 : 0.f, b0 = (t & T_XB) ? q0 : 0.f;
+        const float a1 = (t & T_YF) ? q1 : 0.f, b1 = (t & T_YB) ? q1 : 0.f;
+        f4set(o.q0f, k, a0); f4set(o.q0b, k, b0); f4set(o.q1f, k, a1); f4set(o.q1b, k, b1);
+        f4set(o.own, k, q2 - a0 + b0 - a1 + b1);
+    }
+    return o;
+}
+
+template <int MODE, int SF>
+__global__ void __launch_bounds__(SW_NT, 3) stencil_strip_kernel(const StencilArgs a) {
+    static_assert(MODE == MODE_ITER || MODE == MODE_APPLY, "the warp-strip kernel implements ITER and APPLY");
+    static_assert(SF == 1 || SF == 2 || SF == 4, "sf must divide the group height");
+    __shared__ double red[SW_NT / 32];
+    const Grid& g = a.g;
+    float beta = 0.f;
+    if (MODE == MODE_ITER) {
+        if (!a.sc->active) return;
+        beta = a.sc->beta;
+    }
+    const LightConsts lc = *a.lc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pitch = g.pitch, ny = g.ny;
+    const float inv4 = 1.f / (float)(SF * SF * SF * SF);
+    const unsigned FULL = 0xffffffffu;
+    const int nitems = a.strip_n * a.strip_chunks;
+    double dot = 0.0;
+
+    for (int item = blockIdx.x * (SW_NT / 32) + warp; item < nitems; item += gridDim.x * (SW_NT / 32)) {
+        const int strip = item % a.strip_n, chunk = item / a.strip_n;
+        const int x = 4 * (strip * SW_COLS - 1 + lane);            // x = -4 on lane 0 of strip 0: the zero pad of the previous line
+        const bool colok = x < pitch;
+        const bool writer = (lane >= 1) && (lane <= SW_COLS) && colok;
+        const int jA = chunk * a.strip_cl;
+        const int jB = min(jA + a.strip_cl, ny);
+        const float yy0 = (float)(g.ib0 + x) - g.cy;
+
+        auto load_pn = [&](int j) -> float4 {
+            if (!colok || j > ny) return f4zero();                // line ny is the zero guard line
+            const long long off = (long long)j * pitch + x;
+            if (MODE == MODE_ITER) {
+                const float4 r4 = ld4(a.r + off), p4 = ld4(a.p_in + off);
+                return make_float4(r4.x + beta * p4.x, r4.y + beta * p4.y, r4.z + beta * p4.z, r4.w + beta * p4.w);
+            }
+            return ld4(a.vin + off);
+        };
+        auto load_t = [&](int j) -> unsigned {
+            if (!colok || j > ny) return 0u;
+            return ld_types(a.types, (long long)j * pitch + x);
+        };
+        auto load_w = [&](int j, float4& w0, float4& w1, float4& w2) {
+            if (!colok || j > ny) { w0 = w1 = w2 = f4zero(); return; }
+            const long long off = (long long)j * pitch + x;
+            w0 = ld4(a.w0 + off); w1 = ld4(a.w1 + off); w2 = ld4(a.w2 + off);
+        };
+
+        float4 pl[SW_G + 1], wl0[SW_G + 1], wl1[SW_G + 1], wl2[SW_G + 1];
+        unsigned tl[SW_G + 1];
+        float4 pprev, q0f_prev;
+        {   // prologue: the forward x-rows of line jA-1 reach line jA
+            float4 w0, w1, w2;
+            pprev = load_pn(jA - 1);
+            const unsigned tp = load_t(jA - 1);
+            load_w(jA - 1, w0, w1, w2);
+            pl[0] = load_pn(jA); tl[0] = load_t(jA); load_w(jA, wl0[0], wl1[0], wl2[0]);
+            const float left = __shfl_up_sync(FULL, pprev.w, 1), right = __shfl_down_sync(FULL, pprev.x, 1);
+            const float xx = (float)(g.jb0 + jA - 1) - g.cx;
+            const LineQ q = line_q(lc, g.fx, g.fy, xx, yy0, tp & 0xfbfbfbfbu /* backward x-rows not needed */, pprev, f4zero(),
+                                   pl[0], left, right, w0, w1, w2);
+            q0f_prev = q.q0f;
+        }
+        for (int j0 = jA; j0 < jB; j0 += SW_G) {
+#pragma unroll
+            for (int l = 1; l <= SW_G; l++) {
+                pl[l] = load_pn(j0 + l); tl[l] = load_t(j0 + l); load_w(j0 + l, wl0[l], wl1[l], wl2[l]);
+            }
+            // sf x sf block sums of the group (the K of Kt K)
+            float bs4 = 0.f, bs2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+            if (SF == 4) {
+#pragma unroll
+                for (int l = 0; l < SW_G; l++) bs4 += (pl[l].x + pl[l].y) + (pl[l].z + pl[l].w);
+            } else if (SF == 2) {
+#pragma unroll
+                for (int l = 0; l < SW_G; l++) { bs2[l / 2][0] += pl[l].x + pl[l].y; bs2[l / 2][1] += pl[l].z + pl[l].w; }
+            }
+#pragma unroll
+            for (int l = 0; l < SW_G; l++) {
+                const int j = j0 + l;
+                const float4 pc = pl[l];
+                const float4 up = (l == 0) ? pprev : pl[l > 0 ? l - 1 : 0];
+                const float left = __shfl_up_sync(FULL, pc.w, 1), right = __shfl_down_sync(FULL, pc.x, 1);
+                const float xx = (float)(g.jb0 + j) - g.cx;
+                const LineQ q = line_q(lc, g.fx, g.fy, xx, yy0, tl[l], pc, up, pl[l + 1], left, right, wl0[l], wl1[l], wl2[l]);
+                // backward x-rows of the line below (mask borders only): q0 of line j+1 where it is T_XB
+                float4 q0b_dn = f4zero();
+                const unsigned tn = tl[l + 1];
+                if (__any_sync(FULL, (tn & 0x04040404u) != 0u)) {
+                    const float4 pn = pl[l + 1];
+                    const float ln = __shfl_up_sync(FULL, pn.w, 1), rn = __shfl_down_sync(FULL, pn.x, 1);
+                    const LineQ qn = line_q(lc, g.fx, g.fy, xx + 1.f, yy0, tn & 0xfdfdfdfdu /* forward x-rows not needed */, pn, pc,
+                                            f4zero(), ln, rn, wl0[l + 1], wl1[l + 1], wl2[l + 1]);
+                    q0b_dn = qn.q0b;
+                }
+                const float q1f_left = __shfl_up_sync(FULL, q.q1f.w, 1), q1b_right = __shfl_down_sync(FULL, q.q1b.x, 1);
+                const float q1fv[5] = {q1f_left, q.q1f.x, q.q1f.y, q.q1f.z, q.q1f.w};
+                const float q1bv[5] = {q.q1b.x, q.q1b.y, q.q1b.z, q.q1b.w, q1b_right};
+                float4 out;
+                float dl = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const unsigned t = (tl[l] >> (8 * k)) & 0xffu;
+                    float yv = f4get(q.own, k) + f4get(q0f_prev, k) - f4get(q0b_dn, k) + q1fv[k] - q1bv[k + 1];
+                    if (t & T_LR) {
+                        const float bs = (SF == 4) ? bs4 : ((SF == 2) ? bs2[l / 2][k / 2] : f4get(pc, k));
+                        yv += bs * inv4;
+                    }
+                    if (!(t & T_MASK)) yv = 0.f;
+                    f4set(out, k, yv);
+                    dl += f4get(pc, k) * yv;
+                }
+                if (writer && j < jB) {
+                    const long long off = (long long)j * pitch + x;
+                    st4(a.y + off, out);
+                    if (MODE == MODE_ITER) { st4(a.p_out + off, pc); dot += (double)dl; }
+                }
+                q0f_prev = q.q0f;
+            }
+            pprev = pl[SW_G - 1];
+            pl[0] = pl[SW_G]; tl[0] = tl[SW_G]; wl0[0] = wl0[SW_G]; wl1[0] = wl1[SW_G]; wl2[0] = wl2[SW_G];
+        }
+    }
+
+    if (MODE == MODE_APPLY) return;
+    double total;
+    if (grid_reduce_last<SW_NT>(dot, a.partials, a.ticket, red, total)) {
+        if (threadIdx.x == 0) {                      // alpha = r1 / (p.Ap)       devicecalls.cu:268-269
+            a.sc->dot = total;
+            a.sc->alpha = (float)a.sc->r1 / (float)total;
         }
     }
 }
