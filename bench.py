@@ -249,8 +249,15 @@ def run_ours(args, rank, world, local):
     peak, peak_src = measured_peaks()
     alg_bytes = 28.0 * npix          # reads r, p, w0..2 ; writes p, y  
     achieved = alg_bytes / (prof["cg_stencil"] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "stencil_kernel<MODE_ITER>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get(args.workload, {}).get("cg_operator")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "stencil_strip_kernel<MODE_ITER, sf> (CG operator: p <- r + beta p; y <- (KtK + GtMG) p; p.y)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": prof["cg_stencil"],
                 "other_kernels": {
                     "cg_update_kernel": {"ms": prof["cg_update"], "GBps": 24.0 * npix / (prof["cg_update"] * 1e-3) / 1e9},

@@ -9,7 +9,7 @@
 //   * the host-side loop control with 3 blocking dots per pass -> device-resident CgScalars
 // CG recurrences are exactly those of devicecalls.cu:252-275.
 #pragma once
-#include "srps_common.cuh"
+#include "srps_comm.cuh"
 
 namespace srps {
 
@@ -44,6 +44,7 @@ struct StencilArgs {
     unsigned* ticket;
     int tiles_x, tiles_y;
     int strip_n, strip_chunks, strip_cl;   // warp-strip kernel: strips per line, chunks per strip, lines per chunk
+    PeerComm comm;                         // world == 1: single GPU
 };
 
 struct StencilSmem {
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(CG_NT, 3) stencil_kernel(const StencilArgs a) 
 
     if (MODE == MODE_APPLY) return;
     double total;
-    if (grid_reduce_last<CG_NT>(dot, a.partials, a.ticket, sm.red, total)) {
+    if (grid_reduce_last_world<CG_NT>(dot, a.partials, a.ticket, sm.red, total, a.comm)) {
         if (threadIdx.x == 0) {
             CgScalars* s = a.sc;
             if (MODE == MODE_INIT) {                 // r1 = b.b ; k = 0          devicecalls.cu:242-252
@@ -396,11 +397,14 @@ __global__ void __launch_bounds__(SW_NT, 3) stencil_strip_kernel(const StencilAr
             const LineQ q = line_q(lc, g.fx, g.fy, xx, yy0, tp & 0xfbfbfbfbu /* backward x-rows not needed */, pprev, f4zero(),
                                    pl[0], left, right, w0, w1, w2);
             q0f_prev = q.q0f;
+            // strip partition: keep the search direction on the ghost line above current (recomputed redundantly)
+            if (MODE == MODE_ITER && a.comm.world > 1 && chunk == 0 && writer) st4(a.p_out - pitch + x, pprev);
         }
         for (int j0 = jA; j0 < jB; j0 += SW_G) {
 #pragma unroll
             for (int l = 1; l <= SW_G; l++) {
                 pl[l] = load_pn(j0 + l); tl[l] = load_t(j0 + l); load_w(j0 + l, wl0[l], wl1[l], wl2[l]);
+                if (MODE == MODE_ITER && a.comm.world > 1 && j0 + l == ny && writer) st4(a.p_out + (long long)ny * pitch + x, pl[l]);
             }
             // sf x sf block sums of the group (the K of Kt K)
             float bs4 = 0.f, bs2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
@@ -460,7 +464,7 @@ __global__ void __launch_bounds__(SW_NT, 3) stencil_strip_kernel(const StencilAr
 
     if (MODE == MODE_APPLY) return;
     double total;
-    if (grid_reduce_last<SW_NT>(dot, a.partials, a.ticket, red, total)) {
+    if (grid_reduce_last_world<SW_NT>(dot, a.partials, a.ticket, red, total, a.comm)) {
         if (threadIdx.x == 0) {                      // alpha = r1 / (p.Ap)       devicecalls.cu:268-269
             a.sc->dot = total;
             a.sc->alpha = (float)a.sc->r1 / (float)total;
@@ -475,6 +479,9 @@ struct UpdateArgs {
     CgScalars* sc;
     double* partials;
     unsigned* ticket;
+    PeerComm comm;
+    HaloPeers r_halo;          // strip partition: where the neighbours keep our boundary lines of r
+    int q_per_line;
 };
 
 __global__ void __launch_bounds__(CG_NT, 4) cg_update_kernel(const UpdateArgs a) {
@@ -490,10 +497,14 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_update_kernel(const UpdateArgs a)
         r4.x -= alpha * y4.x; r4.y -= alpha * y4.y; r4.z -= alpha * y4.z; r4.w -= alpha * y4.w;
         st4(a.x + 4 * i, x4);
         st4(a.r + 4 * i, r4);
+        if (a.comm.world > 1) {        // push our first / last line of r into the neighbours' ghost lines (NVLink peer stores)
+            if (a.r_halo.prev_ghost && i < a.q_per_line) st4(a.r_halo.prev_ghost + 4 * i, r4);
+            if (a.r_halo.next_ghost && i >= a.n4 - a.q_per_line) st4(a.r_halo.next_ghost + 4 * (i - (a.n4 - a.q_per_line)), r4);
+        }
         acc += (double)(r4.x * r4.x + r4.y * r4.y) + (double)(r4.z * r4.z + r4.w * r4.w);
     }
     double total;
-    if (grid_reduce_last<CG_NT>(acc, a.partials, a.ticket, red, total)) {
+    if (grid_reduce_last_world<CG_NT>(acc, a.partials, a.ticket, red, total, a.comm)) {
         if (threadIdx.x == 0) {
             CgScalars* s = a.sc;
             s->r0 = s->r1;

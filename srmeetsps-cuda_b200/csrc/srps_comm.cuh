@@ -1,0 +1,108 @@
+// Cross-GPU plumbing for the strip partition (one process per GPU, peers mapped with CUDA IPC).
+//
+// Nothing here exists in the reference (single GPU, SRPS.cu:88).  A scene is cut into strips of
+// lines (image columns); the guard lines of the dense layout (srps_common.cuh) become ghost lines
+// that hold the neighbour's boundary line.  Two exchange mechanisms, both inside our own kernels over
+// NVLink peer memory (no NCCL call on the critical path, no host involvement):
+//
+//   * scalar / small-vector all-reduce by MAILBOX: the last block of a reduction writes the rank's
+//     partial into slot [seq&3][rank] of EVERY peer's mailbox, publishes it with a system-scope
+//     release store of the sequence number, then acquires the world flags of its own mailbox and
+//     sums the partials in rank order -> bit-identical totals on all ranks, so every rank takes the
+//     same CG step and the same `active` decision.
+//   * halo push: boundary lines are stored straight into the neighbour's ghost line through the
+//     mapped peer pointer by the kernel that produces them; the stores are ordered before the
+//     mailbox release by a system-scope fence, so "flag seen" implies "halo arrived".
+#pragma once
+#include "srps_common.cuh"
+
+namespace srps {
+
+constexpr int MAX_RANKS = 8;
+constexpr int MB_SLOTS = 4;
+constexpr int MB_VALS = 800;      // doubles per (slot, source rank): lighting needs n*12 <= 768
+
+struct Mailbox {
+    unsigned long long flag[MB_SLOTS][MAX_RANKS];
+    double val[MB_SLOTS][MAX_RANKS][MB_VALS];
+};
+
+struct PeerComm {
+    int rank, world;
+    Mailbox* local;                      // this rank's mailbox (device memory, IPC-exported)
+    Mailbox* peer[MAX_RANKS];            // every rank's mailbox as mapped here (peer[rank] == local)
+    unsigned long long* seq;             // device-resident reduction counter (same sequence on every rank)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All-reduce (sum, rank order) of n <= MB_VALS doubles held in `vals` (shared or global memory of the
+// calling block).  Called by ALL threads of exactly one block per rank (the reduction's last block);
+// on return vals[0..n) holds the world total.  Needs one __syncthreads-compatible block.
+template <int NT>
+__device__ __forceinline__ void peer_allreduce(const PeerComm& c, double* vals, int n) {
+    if (c.world <= 1) { __syncthreads(); return; }
+    __shared__ unsigned long long s_seq;
+    if (threadIdx.x == 0) s_seq = *c.seq + 1ull;
+    __syncthreads();
+    const unsigned long long seq = s_seq;
+    const int slot = (int)(seq & (MB_SLOTS - 1));
+    // 1. deposit this rank's partial in every rank's mailbox (its own included)
+    for (int e = threadIdx.x; e < n * c.world; e += NT) {
+        const int r = e / n, i = e - r * n;
+        st_relaxed_sys(&c.peer[r]->val[slot][c.rank][i], vals[i]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. publish, 3. wait for the world
+    if (threadIdx.x < c.world) {
+        st_release_sys(&c.peer[threadIdx.x]->flag[slot][c.rank], seq);
+        while (ld_acquire_sys(&c.local->flag[slot][threadIdx.x]) != seq) { }
+    }
+    __syncthreads();
+    // 4. rank-ordered sum: identical bits on every rank
+    for (int i = threadIdx.x; i < n; i += NT) {
+        double t = 0.0;
+        for (int r = 0; r < c.world; r++) t += ld_relaxed_sys(&c.local->val[slot][r][i]);
+        vals[i] = t;
+    }
+    if (threadIdx.x == 0) *c.seq = seq;
+    __syncthreads();
+}
+
+// grid_reduce_last + the cross-rank sum: returns true in the last block of every rank with the WORLD total
+// in `total` (all threads of that block).
+template <int NT>
+__device__ __forceinline__ bool grid_reduce_last_world(double v, double* partials, unsigned* ticket, double* red_smem,
+                                                       double& total, const PeerComm& c) {
+    if (!grid_reduce_last<NT>(v, partials, ticket, red_smem, total)) return false;
+    __shared__ double s_tot;
+    if (threadIdx.x == 0) s_tot = total;
+    __syncthreads();
+    peer_allreduce<NT>(c, &s_tot, 1);
+    total = s_tot;
+    return true;
+}
+
+// Ghost-line destinations in the neighbours' planes (mapped peer pointers), per plane kind.
+struct HaloPeers {
+    float* prev_ghost;     // address of the previous rank's ghost line `ny_prev` of this plane, or nullptr
+    float* next_ghost;     // address of the next rank's ghost line -1 of this plane, or nullptr
+};
+
+}  // namespace srps

@@ -94,7 +94,7 @@ __device__ __forceinline__ bool grid_reduce_last(double v, double* partials, uns
 #pragma unroll
         for (int i = 0; i < NT / 32; i++) b += red_smem[i];
         partials[blockIdx.x] = b;
-        __threadfence();
+        __threadfence_system();       // also orders this block's halo stores into peer memory (srps_comm.cuh)
         unsigned t = atomicAdd(ticket, 1u);
         s_last = (t == gridDim.x - 1);
     }

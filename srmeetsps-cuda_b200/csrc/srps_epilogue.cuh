@@ -7,7 +7,7 @@
 //   energy_depth_kernel   : ||K z - z0s||^2 (devicecalls.cu:762,764,766).
 //   scatter/gather        : reference masked vectors <-> dense grid.
 #pragma once
-#include "srps_common.cuh"
+#include "srps_comm.cuh"
 
 namespace srps {
 
@@ -23,6 +23,7 @@ struct NormalsArgs {
     const float* w[3]; const float* gq[3]; const float* e0;
     double* partials; unsigned* ticket; double* energy_out;   // energy_out[0] = photometric term
     long long n4;
+    PeerComm comm;
 };
 
 template <bool ENERGY>
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(EP_NT, 3) normals_energy_kernel(const NormalsA
     }
     if (ENERGY) {
         double total;
-        if (grid_reduce_last<EP_NT>(acc, a.partials, a.ticket, red, total)) {
+        if (grid_reduce_last_world<EP_NT>(acc, a.partials, a.ticket, red, total, a.comm)) {
             if (threadIdx.x == 0) a.energy_out[0] = total;
         }
     }
@@ -88,6 +89,7 @@ struct EnergyDepthArgs {
     Grid g;
     const float* z; const float* z0lr; const unsigned char* lrmask;
     double* partials; unsigned* ticket; double* energy_out;     // energy_out[1]
+    PeerComm comm;
 };
 
 __global__ void __launch_bounds__(EP_NT, 4) energy_depth_kernel(const EnergyDepthArgs a) {
@@ -108,9 +110,33 @@ __global__ void __launch_bounds__(EP_NT, 4) energy_depth_kernel(const EnergyDept
         acc += (double)(df * df);
     }
     double total;
-    if (grid_reduce_last<EP_NT>(acc, a.partials, a.ticket, red, total)) {
+    if (grid_reduce_last_world<EP_NT>(acc, a.partials, a.ticket, red, total, a.comm)) {
         if (threadIdx.x == 0) a.energy_out[1] = total;
     }
+}
+
+// Strip partition: copy the first / last owned line of up to 8 planes into the neighbours' ghost lines,
+// then a world barrier (mailbox all-reduce of a dummy) so every rank knows its ghosts have arrived.
+struct HaloPushArgs {
+    const float* plane[8];         // origin-offset local planes
+    HaloPeers dst[8];
+    int nplanes, pitch, ny;
+    double* partials; unsigned* ticket;
+    PeerComm comm;
+};
+
+__global__ void __launch_bounds__(EP_NT) halo_push_kernel(const HaloPushArgs a) {
+    __shared__ double red[EP_NT / 32];
+    const int q = a.pitch / 4;
+    for (int e = blockIdx.x * EP_NT + threadIdx.x; e < a.nplanes * 2 * q; e += gridDim.x * EP_NT) {
+        const int pl = e / (2 * q), rem = e - pl * 2 * q, side = rem / q, i = rem - side * q;
+        float* dst = side ? a.dst[pl].next_ghost : a.dst[pl].prev_ghost;
+        if (!dst) continue;
+        const float* src = a.plane[pl] + (side ? (long long)(a.ny - 1) * a.pitch : 0);
+        st4(dst + 4 * i, ld4(src + 4 * i));
+    }
+    double total;
+    grid_reduce_last_world<EP_NT>(0.0, a.partials, a.ticket, red, total, a.comm);
 }
 
 // masked vector -> dense plane (idx = dense offset of masked pixel p)

@@ -11,7 +11,7 @@
 //       (npix*n)-row CSR expansions, SpGEMM producing a diagonal, CG) and the dense B / a1,a2,a3
 //       planes of cuda_based_depth_estimation (devicecalls.cu:550-620) by per-pixel w, g, e0.
 #pragma once
-#include "srps_common.cuh"
+#include "srps_comm.cuh"
 
 namespace srps {
 
@@ -70,6 +70,7 @@ struct GramArgs {
     double* partials;      // [grid][30]
     unsigned* ticket;
     float* gram;           // out: [3][16] full symmetric 4x4 per channel
+    PeerComm comm;
 };
 
 __global__ void __launch_bounds__(ST_NT, 4) lighting_gram_kernel(const GramArgs a) {
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(ST_NT, 4) lighting_gram_kernel(const GramArgs 
         }
     }
     if (grid_reduce_multi<ST_NT, 30>(acc, a.partials, a.ticket, tot, wsm, gridDim.x, blockIdx.x)) {
+        peer_allreduce<ST_NT>(a.comm, tot, 30);          // strip partition: sum over the ranks
         if (threadIdx.x < 48) {
             const int c = threadIdx.x / 16, e = threadIdx.x % 16, x = e / 4, y = e % 4;
             const int lo = x < y ? x : y, hi = x < y ? y : x;
@@ -124,6 +126,7 @@ struct LightArgs {
     float* s;              // in/out [n][3][4]
     LightConsts* lc;       // out
     int max_iter; float tol2;
+    PeerComm comm;
 };
 
 __device__ inline void cg4_reference(const float* A, float* x, float* b, int max_iter, float tol2) {
@@ -204,16 +207,17 @@ __global__ void __launch_bounds__(ST_NT, 2) lighting_reduce_kernel(const LightAr
     if (!grid_reduce_multi<ST_NT, LIGHT_IB * 12>(acc, a.partials, a.ticket, tot, wsm, nblocks, lin)) return;
     // ---- last block: `tot` holds the sum over ALL blocks of all groups (values of different groups
     // were added together), so redo the per-group sums from the partials, then solve.
-    __shared__ float s_new[MAX_IMAGES * 12];
+    __shared__ double s_new[MAX_IMAGES * 12];
     const int gx = gridDim.x;
     for (int e = threadIdx.x; e < a.n_images * 12; e += ST_NT) {
         const int img = e / 12, ck = e % 12;
         const int grp = img / LIGHT_IB, ii = img % LIGHT_IB;
         double b = 0.0;
         for (int bx = 0; bx < gx; bx++) b += __ldcg(a.partials + ((long long)(grp * gx + bx)) * (LIGHT_IB * 12) + ii * 12 + ck);
-        s_new[e] = (float)b;          // Atb for (img, c = ck/4, k = ck%4)
+        s_new[e] = b;                 // Atb for (img, c = ck/4, k = ck%4)
     }
     __syncthreads();
+    peer_allreduce<ST_NT>(a.comm, s_new, a.n_images * 12);   // strip partition: sum over the ranks
     for (int e = threadIdx.x; e < a.n_images * 3; e += ST_NT) {
         const int c = e % 3;
         float A[16], x[4], b[4];
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(ST_NT, 2) lighting_reduce_kernel(const LightAr
         for (int t = 0; t < 4; t++) {                         // residual Atb - AtA s   devicecalls.cu:424
             float ax = 0.f;
             for (int u = 0; u < 4; u++) ax += A[t * 4 + u] * x[u];
-            b[t] = s_new[e * 4 + t] - ax;
+            b[t] = (float)s_new[e * 4 + t] - ax;
         }
         cg4_reference(A, x, b, a.max_iter, a.tol2);           // devicecalls.cu:437
         for (int t = 0; t < 4; t++) a.s[e * 4 + t] = x[t];
