@@ -64,6 +64,11 @@ typedef struct srps_problem {
     int albedo_mode;             /* SRPS_ALBEDO_*                                                     */
     int cg_max_iter;             /* 0 -> 100, the reference's max_iter (devicecalls.cu:231)           */
     float cg_tol;                /* 0 -> 1e-9 (devicecalls.cu:230)                                    */
+    /* Strip partition of ONE scene across the GPUs of a box (no reference equivalent: SRPS.cu:88 is
+     * single-GPU).  world <= 1: the context owns the whole image.  world > 1: `mask` is still the GLOBAL
+     * mask; this context owns image columns [strip_j0, strip_j1) (multiples of 4), rank in [0, world). */
+    int strip_j0, strip_j1;
+    int rank, world;
 } srps_problem;
 
 /* Per-phase device times (cudaEvent, ms) of the last srps_outer_iteration + launch counters. */
@@ -108,6 +113,22 @@ int  srps_run(srps_ctx* ctx, int max_outer, float tol, int fixed_iters, float* e
 
 int  srps_get_timings(const srps_ctx* ctx, srps_timings* out);
 int  srps_synchronize(srps_ctx* ctx);
+
+/* ---- strip partition (one process per GPU; peers are mapped with CUDA IPC over NVLink) -------------
+ * 1. every rank: srps_ctx_create with its strip, then srps_dist_export -> an opaque blob;
+ * 2. the caller all-gathers the blobs (torch.distributed / MPI / files) in rank order;
+ * 3. every rank: srps_dist_connect(ctx, all_blobs, world).
+ * Afterwards the operators above are COLLECTIVE: every rank must call them in the same order.
+ * Host vectors passed to a strip context cover only its pixels: srps_pixel_range gives the half-open
+ * ranges [p0,p1) of the global masked vector and [q0,q1) of the global LR masked vector it owns
+ * (strips cut the column-major masked order into contiguous runs). */
+int  srps_dist_blob_size(void);
+int  srps_dist_export(srps_ctx* ctx, void* blob);
+int  srps_dist_connect(srps_ctx* ctx, const void* blobs, int world);
+int  srps_pixel_range(const srps_ctx* ctx, long long* p0, long long* p1, long long* q0, long long* q1);
+/* srps_upload_state with an explicit plane stride (floats) between the n*c planes of I: a strip context
+ * reads its run [p0,p1) out of each plane of the global stack (pass I + p0, stride = global npix). */
+int  srps_upload_state_strided(srps_ctx* ctx, const float* I, long long plane_stride, const float* z, const float* z0s);
 
 /* Device-side stopwatch on the context's stream (cudaEvent): everything the context enqueues
  * between start and stop -- uploads, kernels, downloads -- is inside the measured interval. */

@@ -18,7 +18,8 @@ class Problem(C.Structure):
     _fields_ = [("h", C.c_int), ("w", C.c_int), ("n_images", C.c_int), ("n_channels", C.c_int), ("sf", C.c_int),
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
                 ("mask", C.c_void_p), ("device", C.c_int), ("albedo_mode", C.c_int),
-                ("cg_max_iter", C.c_int), ("cg_tol", C.c_float)]
+                ("cg_max_iter", C.c_int), ("cg_tol", C.c_float),
+                ("strip_j0", C.c_int), ("strip_j1", C.c_int), ("rank", C.c_int), ("world", C.c_int)]
 
 
 class Timings(C.Structure):
@@ -45,6 +46,12 @@ EXPORTS = {
     "srps_run": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "srps_get_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "srps_synchronize": (C.c_int, [C.c_void_p]),
+    "srps_dist_blob_size": (C.c_int, []),
+    "srps_dist_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "srps_dist_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "srps_pixel_range": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+                                   C.POINTER(C.c_longlong)]),
+    "srps_upload_state_strided": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "srps_timer_start": (C.c_int, [C.c_void_p]),
     "srps_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "srps_profile_kernels": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),

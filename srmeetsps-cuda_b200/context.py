@@ -23,9 +23,11 @@ def _ptr(a):
 
 class Context:
     def __init__(self, mask, n_images, sf, K, device=0, albedo_mode="closed_form", cg_max_iter=0, cg_tol=0.0,
-                 n_channels=3):
+                 n_channels=3, strip=None, rank=0, world=1):
         """mask: (h, w) array, non-zero = inside.  K: the reference's column-major 3x3
-        (K[0]=fx, K[4]=fy, K[6]=cx, K[7]=cy; Utilities.cpp:364-373)."""
+        (K[0]=fx, K[4]=fy, K[6]=cx, K[7]=cy; Utilities.cpp:364-373).
+        strip=(j0, j1), rank, world: this context owns image columns [j0, j1) of the GLOBAL mask
+        (strip partition across GPUs, see dist.py); call dist_connect before any operator."""
         self.lib = L.load()
         mask = np.asarray(mask)
         h, w = mask.shape
@@ -33,7 +35,8 @@ class Context:
         K = np.asarray(K, dtype=np.float64).ravel()
         mode = {"closed_form": L.SRPS_ALBEDO_CLOSED_FORM, "reference_cg": L.SRPS_ALBEDO_REFERENCE_CG}[albedo_mode]
         self.prob = L.Problem(h, w, int(n_images), int(n_channels), int(sf), float(K[0]), float(K[4]), float(K[6]),
-                              float(K[7]), _ptr(self._mask_cm), int(device), mode, int(cg_max_iter), float(cg_tol))
+                              float(K[7]), _ptr(self._mask_cm), int(device), mode, int(cg_max_iter), float(cg_tol),
+                              int(strip[0]) if strip else 0, int(strip[1]) if strip else 0, int(rank), int(world))
         self.h, self.w, self.n, self.c, self.sf = h, w, int(n_images), int(n_channels), int(sf)
         self._ctx = C.c_void_p()
         rc = self.lib.srps_ctx_create(C.byref(self.prob), C.byref(self._ctx))
@@ -63,6 +66,29 @@ class Context:
     def _ck(self, rc, what):
         if rc != 0:
             raise SRPSError(f"{what} failed ({rc}): {self.lib.srps_last_error(self._ctx).decode()}")
+
+    # -- strip partition ------------------------------------------------------------------------
+    def dist_export(self) -> bytes:
+        buf = C.create_string_buffer(self.lib.srps_dist_blob_size())
+        self._ck(self.lib.srps_dist_export(self._ctx, buf), "srps_dist_export")
+        return buf.raw
+
+    def dist_connect(self, blobs):
+        raw = b"".join(blobs)
+        assert len(raw) == len(blobs) * self.lib.srps_dist_blob_size()
+        self._ck(self.lib.srps_dist_connect(self._ctx, raw, len(blobs)), "srps_dist_connect")
+
+    def pixel_range(self):
+        v = [C.c_longlong(0) for _ in range(4)]
+        self._ck(self.lib.srps_pixel_range(self._ctx, *[C.byref(x) for x in v]), "srps_pixel_range")
+        return tuple(int(x.value) for x in v)
+
+    def upload_state_strided(self, I_first, plane_stride, z, z0s):
+        """I_first: 1-D float32 view starting at this strip's first pixel of plane 0 of the global stack."""
+        z = np.ascontiguousarray(z, dtype=np.float32); z0s = np.ascontiguousarray(z0s, dtype=np.float32)
+        assert I_first.dtype == np.float32 and z.shape == (self.npix,) and z0s.shape == (self.npixs,)
+        self._ck(self.lib.srps_upload_state_strided(self._ctx, _ptr(I_first), int(plane_stride), _ptr(z), _ptr(z0s)),
+                 "srps_upload_state_strided")
 
     # -- state ----------------------------------------------------------------------------------
     def upload_state(self, I, z, z0s):

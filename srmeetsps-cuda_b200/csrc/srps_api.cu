@@ -63,6 +63,22 @@ struct srps_ctx {
     long long n4 = 0;
     cudaGraphExec_t cg_graph = nullptr;
     int use_graph = 1;
+    // strip partition
+    int rank = 0, world = 1;
+    bool connected = false;
+    long long pix0 = 0, lr0 = 0;           // global masked index of the first owned HR / LR pixel
+    PeerComm comm{};                        // world == 1 unless srps_dist_connect succeeded
+    Mailbox* mailbox = nullptr;
+    unsigned long long* seq = nullptr;
+    void* peer_planes[MAX_RANKS]{};         // mapped plane allocations of the neighbours
+    int peer_ny[MAX_RANKS]{};
+    long long peer_plane[MAX_RANKS]{};
+};
+
+struct DistBlob {
+    cudaIpcMemHandle_t planes, mbox;
+    int rank, ny, pitch, pad;
+    long long plane;
 };
 
 #define CK(call)                                                                                   \
@@ -88,6 +104,8 @@ static int fail(srps_ctx* ctx, int code, const std::string& msg) {
 }
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static HaloPeers halo_peers(const srps_ctx* ctx, const float* local_plane);
+static int halo_push(srps_ctx* ctx, std::initializer_list<const float*> planes);
 
 extern "C" const char* srps_build_info(void) { return "srps-b200 sm_100a " __DATE__ " " __TIME__; }
 extern "C" const char* srps_last_error(const srps_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -102,6 +120,11 @@ extern "C" void srps_ctx_destroy(srps_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->cg_graph) cudaGraphExecDestroy(ctx->cg_graph);
+    for (int r = 0; r < MAX_RANKS; r++) {
+        if (ctx->peer_planes[r]) cudaIpcCloseMemHandle(ctx->peer_planes[r]);
+        if (ctx->connected && r != ctx->rank && r < ctx->world && ctx->comm.peer[r]) cudaIpcCloseMemHandle(ctx->comm.peer[r]);
+    }
+    cudaFree(ctx->mailbox); cudaFree(ctx->seq);
     cudaFree(ctx->plane_base); cudaFree(ctx->types_base); cudaFree(ctx->lrmask); cudaFree(ctx->idx); cudaFree(ctx->idx_lr);
     cudaFree(ctx->I_base); cudaFree(ctx->z0lr); cudaFree(ctx->s); cudaFree(ctx->gram); cudaFree(ctx->lc); cudaFree(ctx->sc);
     cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->energy); cudaFree(ctx->staging); cudaFree(ctx->U);
@@ -142,7 +165,28 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     Grid& g = ctx->g;
     g.sf = sf;
     g.ib0 = imin / sf * sf; g.jb0 = jmin / sf * sf;
-    const int ib1 = (imax + sf) / sf * sf, jb1 = (jmax + sf) / sf * sf;
+    int ib1 = (imax + sf) / sf * sf, jb1 = (jmax + sf) / sf * sf;
+    ctx->rank = 0; ctx->world = 1;
+    if (prob->world > 1) {
+        // strip partition: the pixel-row range stays the GLOBAL bounding range (same pitch on every rank),
+        // the lines are exactly the owned image columns
+        ctx->rank = prob->rank; ctx->world = prob->world;
+        g.jb0 = prob->strip_j0; jb1 = prob->strip_j1;
+        npix = 0;
+        long long before = 0, lr_before = 0;
+        for (int j = 0; j < jb1; j++)
+            for (int i = 0; i < h; i++)
+                if (m[(size_t)i + (size_t)j * h]) { if (j < g.jb0) before++; else npix++; }
+        for (int q = 0; q < g.jb0 / sf; q++)
+            for (int r = 0; r < h / sf; r++) {
+                bool all = true;
+                for (int l = 0; l < sf && all; l++)
+                    for (int k = 0; k < sf; k++)
+                        if (!m[(size_t)(r * sf + k) + (size_t)(q * sf + l) * h]) { all = false; break; }
+                lr_before += all;
+            }
+        ctx->pix0 = before; ctx->lr0 = lr_before;
+    }
     g.nx = ib1 - g.ib0; g.ny = jb1 - g.jb0;
     g.pitch = round_up(g.nx + 1, 32);
     g.lnx = g.nx / sf; g.lny = g.ny / sf; g.lpitch = round_up(g.lnx, 4);
@@ -156,7 +200,7 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     ctx->full_rect = (npix == (long long)g.nx * g.ny);
 
     std::vector<unsigned char> types((size_t)g.plane, 0);
-    std::vector<int> idx((size_t)npix);
+    std::vector<int> idx((size_t)std::max<long long>(npix, 1));
     std::vector<unsigned char> lrmask((size_t)g.lny * g.lpitch, 0);
     std::vector<int> idx_lr;
     auto M = [&](int i, int j) -> bool { return i >= 0 && i < h && j >= 0 && j < w && m[(size_t)i + (size_t)j * h]; };
@@ -171,9 +215,17 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         }
     ctx->npixs = (int)idx_lr.size();
     size_t pcount = 0;
-    for (int j = g.jb0; j < jb1 && j < w; j++)
+    const int ghost = ctx->world > 1 ? 1 : 0;          // ghost lines carry the neighbour strip's stencil types
+    for (int j = g.jb0 - ghost; j < jb1 + ghost && j < w; j++)
         for (int i = g.ib0; i < ib1 && i < h; i++) {
-            if (!M(i, j)) continue;
+            if (j < 0 || !M(i, j)) continue;
+            if (j < g.jb0 || j >= jb1) {               // ghost line: types only
+                unsigned char t = T_MASK;
+                if (M(i, j + 1)) t |= T_XF; else if (M(i, j - 1)) t |= T_XB;
+                if (M(i + 1, j)) t |= T_YF; else if (M(i - 1, j)) t |= T_YB;
+                types[(size_t)(g.origin() + (long long)(j - g.jb0) * g.pitch + (i - g.ib0))] = t;
+                continue;
+            }
             unsigned char t = T_MASK;
             if (M(i, j + 1)) t |= T_XF; else if (M(i, j - 1)) t |= T_XB;        // SRPS.cu:39-46
             if (M(i + 1, j)) t |= T_YF; else if (M(i - 1, j)) t |= T_YB;        // SRPS.cu:31-38
@@ -224,6 +276,11 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     CK(cudaMalloc(&ctx->sc, sizeof(CgScalars) * 4));
     CK(cudaMalloc(&ctx->tickets, sizeof(unsigned) * 8));
     CK(cudaMemsetAsync(ctx->tickets, 0, sizeof(unsigned) * 8, ctx->stream));
+    CK(cudaMalloc(&ctx->mailbox, sizeof(Mailbox)));
+    CK(cudaMemsetAsync(ctx->mailbox, 0, sizeof(Mailbox), ctx->stream));
+    CK(cudaMalloc(&ctx->seq, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->seq, 0, sizeof(unsigned long long), ctx->stream));
+    ctx->comm.rank = 0; ctx->comm.world = 1; ctx->comm.local = ctx->mailbox; ctx->comm.seq = ctx->seq;
     CK(cudaMalloc(&ctx->energy, sizeof(double) * 2));
     CK(cudaMallocHost(&ctx->h_energy, sizeof(double) * 2));
     CK(cudaMallocHost(&ctx->h_sc, sizeof(CgScalars) * 4));
@@ -245,7 +302,7 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     ctx->grid_stencil = std::min(ctx->tiles_x * ctx->tiles_y, ctx->sm_count * std::max(1, occ));
     {   // warp-strip operator (sf <= 4): strips of 30 float4 columns x chunks of lines, one warp each
         const char* si = getenv("SRPS_STENCIL");
-        ctx->use_strip = (sf <= 4) && !(si && strcmp(si, "tile") == 0);
+        ctx->use_strip = (sf <= 4) && (!(si && strcmp(si, "tile") == 0) || ctx->world > 1);
         const int nq = (g.nx + 3) / 4;
         ctx->strip_n = (nq + SW_COLS - 1) / SW_COLS;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stencil_strip_kernel<MODE_ITER, 4>, SW_NT, 0));
@@ -290,6 +347,13 @@ extern "C" int srps_ctx_create(const srps_problem* prob, srps_ctx** out) {
     if (prob->h % sf || prob->w % sf) return fail(nullptr, SRPS_E_INVALID, "h and w must be multiples of sf");
     if (prob->albedo_mode != SRPS_ALBEDO_CLOSED_FORM && prob->albedo_mode != SRPS_ALBEDO_REFERENCE_CG)
         return fail(nullptr, SRPS_E_INVALID, "bad albedo_mode");
+    if (prob->world > 1) {
+        if (prob->world > MAX_RANKS || prob->rank < 0 || prob->rank >= prob->world) return fail(nullptr, SRPS_E_INVALID, "bad rank / world (<= 8 ranks)");
+        if (sf > 4) return fail(nullptr, SRPS_E_INVALID, "strip partition needs sf <= 4 (warp-strip operator kernel)");
+        if (prob->albedo_mode != SRPS_ALBEDO_CLOSED_FORM) return fail(nullptr, SRPS_E_INVALID, "strip partition supports the closed-form albedo only");
+        if (prob->strip_j0 < 0 || prob->strip_j1 > prob->w || prob->strip_j0 >= prob->strip_j1 || prob->strip_j0 % 4 || prob->strip_j1 % 4)
+            return fail(nullptr, SRPS_E_INVALID, "strip_j0 / strip_j1 must be multiples of 4 inside [0, w]");
+    }
     srps_ctx* ctx = new srps_ctx();
     int rc = ctx_create_impl(ctx, prob);
     if (rc != 0) {
@@ -337,6 +401,7 @@ static int launch_normals(srps_ctx* ctx, bool energy, float* const* Nout, float*
     for (int c = 0; c < 3; c++) { a.N[c] = Nout[c]; a.w[c] = ctx->w[c]; a.gq[c] = ctx->gq[c]; }
     a.dz = dzout; a.lc = ctx->lc; a.e0 = ctx->e0;
     a.partials = ctx->partials; a.ticket = ctx->tickets + 0; a.energy_out = ctx->energy; a.n4 = ctx->n4;
+    a.comm = ctx->comm;
     if (energy) LAUNCH(ctx, normals_energy_kernel<true>, ctx->grid_ep, EP_NT, a);
     else LAUNCH(ctx, normals_energy_kernel<false>, ctx->grid_ep, EP_NT, a);
     CK(cudaGetLastError());
@@ -365,21 +430,27 @@ extern "C" int srps_upload_images_u8(srps_ctx* ctx, const unsigned char* I8) {
 }
 
 extern "C" int srps_upload_state(srps_ctx* ctx, const float* I, const float* z, const float* z0s) {
+    return srps_upload_state_strided(ctx, I, ctx ? ctx->npix : 0, z, z0s);
+}
+
+extern "C" int srps_upload_state_strided(srps_ctx* ctx, const float* I, long long plane_stride, const float* z, const float* z0s) {
     if (!ctx || !z || !z0s) return fail(ctx, SRPS_E_INVALID, "null argument");
+    if (I && plane_stride < ctx->npix) return fail(ctx, SRPS_E_INVALID, "plane_stride smaller than the pixel count");
     CK(cudaSetDevice(ctx->device));
     const Grid& g = ctx->g;
     if (I) {
         const int planes = ctx->n * 3;
         if (ctx->full_rect) {
             for (int pl = 0; pl < planes; pl++)
-                CK(cudaMemcpy2DAsync(ctx->I + (long long)pl * g.plane, sizeof(float) * g.pitch, I + (size_t)pl * ctx->npix,
+                CK(cudaMemcpy2DAsync(ctx->I + (long long)pl * g.plane, sizeof(float) * g.pitch, I + (size_t)pl * plane_stride,
                                      sizeof(float) * g.nx, sizeof(float) * g.nx, g.ny, cudaMemcpyHostToDevice, ctx->stream));
         } else {
             const size_t per = sizeof(float) * (size_t)ctx->npix;
             const int chunk = (int)std::max<size_t>(1, std::min<size_t>(planes, ctx->staging_bytes / per));
             for (int p0 = 0; p0 < planes; p0 += chunk) {
                 const int np = std::min(chunk, planes - p0);
-                CK(cudaMemcpyAsync(ctx->staging, I + (size_t)p0 * ctx->npix, per * np, cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaMemcpy2DAsync(ctx->staging, per, I + (size_t)p0 * plane_stride, sizeof(float) * (size_t)plane_stride, per, np,
+                                     cudaMemcpyHostToDevice, ctx->stream));
                 for (int k = 0; k < np; k++)
                     LAUNCH(ctx, scatter_kernel, (ctx->npix + 255) / 256, 256, (const float*)ctx->staging + (size_t)k * ctx->npix,
                            ctx->idx, ctx->I + (long long)(p0 + k) * g.plane, ctx->npix);
@@ -409,6 +480,7 @@ extern "C" int srps_upload_state(srps_ctx* ctx, const float* I, const float* z, 
         LAUNCH(ctx, fill_masked_kernel, (ctx->npix + 255) / 256, 256, ctx->idx, ctx->rho[c], ctx->npix, 0.5f);
     CK(cudaGetLastError());
     // first normals: zx, zy, normal_init   SRPS.cu:264-270
+    if ((rc = halo_push(ctx, {ctx->z}))) return rc;
     if ((rc = launch_normals(ctx, false, ctx->N, ctx->dz))) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_state = true;
@@ -499,7 +571,7 @@ extern "C" int srps_lighting(srps_ctx* ctx) {
     LightArgs la{};
     for (int c = 0; c < 3; c++) { ga.rho[c] = la.rho[c] = ctx->rho[c]; ga.N[c] = la.N[c] = ctx->N[c]; }
     ga.n4 = la.n4 = ctx->n4;
-    ga.partials = ctx->partials; ga.ticket = ctx->tickets + 1; ga.gram = ctx->gram;
+    ga.partials = ctx->partials; ga.ticket = ctx->tickets + 1; ga.gram = ctx->gram; ga.comm = ctx->comm; la.comm = ctx->comm;
     LAUNCH(ctx, lighting_gram_kernel, ctx->grid_gram, ST_NT, ga);
     la.I = ctx->I; la.plane = ctx->g.plane; la.n_images = ctx->n;
     la.partials = ctx->partials; la.ticket = ctx->tickets + 2; la.gram = ctx->gram; la.s = ctx->s; la.lc = ctx->lc;
@@ -555,6 +627,38 @@ static void fill_stencil_args(srps_ctx* ctx, StencilArgs& sa) {
     sa.z0lr = ctx->z0lr; sa.sc = ctx->sc; sa.partials = ctx->partials; sa.ticket = ctx->tickets + 4;
     sa.tiles_x = ctx->tiles_x; sa.tiles_y = ctx->tiles_y;
     sa.strip_n = ctx->strip_n; sa.strip_chunks = ctx->strip_chunks; sa.strip_cl = ctx->strip_cl;
+    sa.comm = ctx->comm;
+}
+
+// Ghost-line addresses of plane `local_plane` inside the two neighbours' (mapped) plane allocations.
+static HaloPeers halo_peers(const srps_ctx* ctx, const float* local_plane) {
+    HaloPeers hp{nullptr, nullptr};
+    if (!ctx->connected) return hp;
+    const Grid& g = ctx->g;
+    const long long k = (local_plane - g.origin() - ctx->plane_base) / g.plane;      // plane index: same order on every rank
+    if (ctx->rank > 0) {
+        const int q = ctx->rank - 1;
+        hp.prev_ghost = (float*)ctx->peer_planes[q] + k * ctx->peer_plane[q] + g.origin() + (long long)ctx->peer_ny[q] * g.pitch;
+    }
+    if (ctx->rank + 1 < ctx->world) {
+        const int q = ctx->rank + 1;
+        hp.next_ghost = (float*)ctx->peer_planes[q] + k * ctx->peer_plane[q] + g.origin() - g.pitch;
+    }
+    return hp;
+}
+
+// push the boundary lines of the given planes into the neighbours' ghost lines + world barrier
+static int halo_push(srps_ctx* ctx, std::initializer_list<const float*> planes) {
+    if (ctx->world <= 1) return 0;
+    if (!ctx->connected) return fail(ctx, SRPS_E_STATE, "strip context used before srps_dist_connect");
+    HaloPushArgs a{};
+    int n = 0;
+    for (const float* pl : planes) { a.plane[n] = pl; a.dst[n] = halo_peers(ctx, pl); n++; }
+    a.nplanes = n; a.pitch = ctx->g.pitch; a.ny = ctx->g.ny; a.partials = ctx->partials; a.ticket = ctx->tickets + 7; a.comm = ctx->comm;
+    const int blocks = std::max(1, std::min(64, (n * 2 * (ctx->g.pitch / 4) + EP_NT - 1) / EP_NT));
+    LAUNCH(ctx, halo_push_kernel, blocks, EP_NT, a);
+    CK(cudaGetLastError());
+    return 0;
 }
 
 // y = A p (MODE_ITER: with the fused p-update and p.y) through the kernel variant of this context
@@ -601,16 +705,33 @@ extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
     StencilArgs sa{};
     fill_stencil_args(ctx, sa);
     // residual r = Kt z0s + At B - (KtK + AtA) z   devicecalls.cu:743-745,758  (written to `r`)
+    int rc;
+    if ((rc = halo_push(ctx, {ctx->z, ctx->w[0], ctx->w[1], ctx->w[2], ctx->gq[0]}))) return rc;    // strip partition: ghosts of the operands
     StencilArgs si = sa;
     si.y = ctx->r;
     LAUNCH(ctx, stencil_kernel<MODE_INIT>, ctx->grid_stencil, CG_NT, si);
     CK(cudaGetLastError());
+    if ((rc = halo_push(ctx, {ctx->r}))) return rc;
     UpdateArgs ua{};
     ua.x = ctx->z; ua.r = ctx->r; ua.p = ctx->p; ua.y = ctx->y; ua.n4 = ctx->n4; ua.sc = ctx->sc; ua.partials = ctx->partials;
     ua.ticket = ctx->tickets + 5;
+    ua.comm = ctx->comm; ua.r_halo = halo_peers(ctx, ctx->r); ua.q_per_line = ctx->g.pitch / 4;
     const int passes = ctx->h_sc[0].max_iter + 1;     // k <= max_iter -> max_iter + 1 passes   devicecalls.cu:252
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
-    if (ctx->use_graph) {
+    if (getenv("SRPS_TRACE")) {
+        // debugging aid: one pass at a time, CG scalars printed after each (no graph)
+        for (int k = 0; k < passes; k++) {
+            StencilArgs s1 = sa; UpdateArgs u1 = ua;
+            s1.p_in = (k & 1) ? ctx->p2 : ctx->p; s1.p_out = (k & 1) ? ctx->p : ctx->p2; u1.p = s1.p_out;
+            launch_operator<MODE_ITER>(ctx, s1);
+            LAUNCH(ctx, cg_update_kernel, ctx->grid_update, CG_NT, u1);
+            CK(cudaMemcpyAsync(ctx->h_sc, ctx->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            fprintf(stderr, "[srps rank %d] pass %3d: r1 %.6e r0 %.6e p.Ap %.6e alpha %.6e beta %.6e k %d active %d\n", ctx->rank, k,
+                    ctx->h_sc[0].r1, ctx->h_sc[0].r0, ctx->h_sc[0].dot, ctx->h_sc[0].alpha, ctx->h_sc[0].beta, ctx->h_sc[0].k, ctx->h_sc[0].active);
+            if (!ctx->h_sc[0].active) break;
+        }
+    } else if (ctx->use_graph) {
         if (!ctx->cg_graph) {
             cudaGraph_t graph = nullptr;
             const long long before = ctx->launches;
@@ -629,11 +750,11 @@ extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
     }
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
     // energy with lagged A,B and the new z (devicecalls.cu:762-767) + the normals of the new z
-    int rc;
+    if ((rc = halo_push(ctx, {ctx->z}))) return rc;
     if ((rc = launch_normals(ctx, true, ctx->N_new, ctx->dz_new))) return rc;
     EnergyDepthArgs ea{};
     ea.g = ctx->g; ea.z = ctx->z; ea.z0lr = ctx->z0lr; ea.lrmask = ctx->lrmask; ea.partials = ctx->partials + 0;
-    ea.ticket = ctx->tickets + 6; ea.energy_out = ctx->energy;
+    ea.ticket = ctx->tickets + 6; ea.energy_out = ctx->energy; ea.comm = ctx->comm;
     const long long ncell = (long long)ctx->g.lny * ctx->g.lnx;
     LAUNCH(ctx, energy_depth_kernel, (int)std::min<long long>((ncell + EP_NT - 1) / EP_NT, ctx->sm_count * 4), EP_NT, ea);
     CK(cudaGetLastError());
@@ -655,6 +776,8 @@ extern "C" int srps_normals(srps_ctx* ctx) {
     if (!ctx->have_state) return fail(ctx, SRPS_E_STATE, "no state uploaded");
     CK(cudaSetDevice(ctx->device));
     if (ctx->pending_normals) return apply_pending_normals(ctx);
+    int rc;
+    if ((rc = halo_push(ctx, {ctx->z}))) return rc;
     return launch_normals(ctx, false, ctx->N, ctx->dz);
 }
 
@@ -723,6 +846,7 @@ extern "C" int srps_apply_depth_operator(srps_ctx* ctx, const float* p_host, flo
     CK(cudaSetDevice(ctx->device));
     int rc;
     if ((rc = scatter_from_host(ctx, p_host, ctx->p))) return rc;     // clobbers the CG work planes p, y
+    if ((rc = halo_push(ctx, {ctx->p, ctx->w[0], ctx->w[1], ctx->w[2]}))) return rc;
     StencilArgs sa{};
     fill_stencil_args(ctx, sa);
     sa.vin = ctx->p;
@@ -770,6 +894,7 @@ extern "C" int srps_profile_kernels(srps_ctx* ctx, int reps, float* out_ms) {
     UpdateArgs ua{};
     ua.x = ctx->y; ua.r = ctx->r; ua.p = ctx->p; ua.y = ctx->p2; ua.n4 = ctx->n4; ua.sc = ctx->sc; ua.partials = ctx->partials;
     ua.ticket = ctx->tickets + 5;
+    ua.comm = ctx->comm; ua.r_halo = halo_peers(ctx, ctx->r); ua.q_per_line = ctx->g.pitch / 4;
     // warm-up + stencil alone
     for (int pass = 0; pass < 2; pass++) {
         if (pass == 1) CK(cudaEventRecord(e0, ctx->stream));
@@ -828,5 +953,53 @@ extern "C" int srps_profile_kernels(srps_ctx* ctx, int reps, float* out_ms) {
     ctx->coeffs_valid = false;
     if (rc) return rc;
     if (!still_active) return fail(ctx, SRPS_E_STATE, "profile: CG scalars went non-finite, stencil timing invalid");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// strip partition: CUDA IPC wiring of the peers
+// ------------------------------------------------------------------------------------------------
+extern "C" int srps_dist_blob_size(void) { return (int)sizeof(DistBlob); }
+
+extern "C" int srps_dist_export(srps_ctx* ctx, void* blob) {
+    if (!ctx || !blob) return fail(ctx, SRPS_E_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    DistBlob b;
+    memset(&b, 0, sizeof b);
+    CK(cudaIpcGetMemHandle(&b.planes, ctx->plane_base));
+    CK(cudaIpcGetMemHandle(&b.mbox, ctx->mailbox));
+    b.rank = ctx->rank; b.ny = ctx->g.ny; b.pitch = ctx->g.pitch; b.plane = ctx->g.plane;
+    memcpy(blob, &b, sizeof b);
+    return 0;
+}
+
+extern "C" int srps_dist_connect(srps_ctx* ctx, const void* blobs, int world) {
+    if (!ctx || !blobs) return fail(ctx, SRPS_E_INVALID, "null argument");
+    if (world != ctx->world || world < 2) return fail(ctx, SRPS_E_INVALID, "world does not match the context's strip partition");
+    CK(cudaSetDevice(ctx->device));
+    const DistBlob* b = (const DistBlob*)blobs;
+    for (int r = 0; r < world; r++) {
+        if (b[r].rank != r) return fail(ctx, SRPS_E_INVALID, "blobs must be gathered in rank order");
+        if (b[r].pitch != ctx->g.pitch) return fail(ctx, SRPS_E_INVALID, "ranks disagree on the line pitch (different global masks?)");
+        ctx->peer_ny[r] = b[r].ny; ctx->peer_plane[r] = b[r].plane;
+        if (r == ctx->rank) { ctx->comm.peer[r] = ctx->mailbox; continue; }
+        void* mb = nullptr;
+        CK(cudaIpcOpenMemHandle(&mb, b[r].mbox, cudaIpcMemLazyEnablePeerAccess));
+        ctx->comm.peer[r] = (Mailbox*)mb;
+        if (r == ctx->rank - 1 || r == ctx->rank + 1)
+            CK(cudaIpcOpenMemHandle(&ctx->peer_planes[r], b[r].planes, cudaIpcMemLazyEnablePeerAccess));
+    }
+    ctx->comm.rank = ctx->rank; ctx->comm.world = world; ctx->comm.local = ctx->mailbox; ctx->comm.seq = ctx->seq;
+    ctx->connected = true;
+    if (ctx->cg_graph) { cudaGraphExecDestroy(ctx->cg_graph); ctx->cg_graph = nullptr; }
+    return 0;
+}
+
+extern "C" int srps_pixel_range(const srps_ctx* ctx, long long* p0, long long* p1, long long* q0, long long* q1) {
+    if (!ctx) return SRPS_E_INVALID;
+    if (p0) *p0 = ctx->pix0;
+    if (p1) *p1 = ctx->pix0 + ctx->npix;
+    if (q0) *q0 = ctx->lr0;
+    if (q1) *q1 = ctx->lr0 + ctx->npixs;
     return 0;
 }

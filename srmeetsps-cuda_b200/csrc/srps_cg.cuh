@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(CG_NT, 3) stencil_kernel(const StencilArgs a) 
             const int which = tid / (TX / 4), q4 = tid % (TX / 4);
             const int ly = which ? TY + 1 : 0;
             const int j = y0 + ly - 1, x = x0 + 4 * q4;
-            const bool ok = (j >= 0) && (j < ny) && (x < pitch);
+            const bool ok = (j <= ny) && (x < pitch);      // j = -1 / ny: guard lines (zero) or, in a strip partition, ghost lines
             const long long off = (long long)j * pitch + x;
             float4 w0 = f4zero(), w1 = f4zero(), w2 = f4zero(), gg0 = f4zero();
             if (ok) {
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(CG_NT, 3) stencil_kernel(const StencilArgs a) 
                         yv += bs * inv4;
                     }
                 }
-                if (!(t & T_MASK)) yv = 0.f;
+                if (!(t & T_MASK) || !ok) yv = 0.f;      // !ok: lines >= ny of a partial tile (a ghost line in a strip partition)
                 f4set(out, k, yv);
                 if (MODE == MODE_INIT) dot += (double)(yv * yv);
                 else dot += (double)(pc_keep[rep][k] * yv);
