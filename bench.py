@@ -196,13 +196,21 @@ def run_ours(args, rank, world, local):
     from srmeetsps_cuda_b200 import Context
     from srmeetsps_cuda_b200.synth import synth_scene_torch
 
+    from srmeetsps_cuda_b200.dist import make_strip_context, strip_bounds
     h, w, sf, n, seed = WORKLOADS[args.workload]
     torch.cuda.set_device(local)
-    # N > 1: independent replicas, one scene per GPU (BASELINE config 5 pattern; the strip partition
-    # of one scene across GPUs is not implemented yet -- DESIGN.md §Multi-GPU)
-    sc = synth_scene_torch(h, w, sf, n, seed + rank, device=f"cuda:{local}")
-    npix = h * w
-    ctx = Context(sc["mask"], n, sf, sc["K"], device=local, albedo_mode=args.albedo)
+    strips = world > 1 and args.parallelism == "strips"
+    if strips:
+        # ONE scene, strip-partitioned along the image columns (BASELINE config 4 at 2/4/8 GPUs): ghost lines and
+        # CG scalars travel inside the library's kernels over NVLink peer memory (csrc/srps_comm.cuh)
+        j0, j1 = strip_bounds(w, world)[rank]
+        sc = synth_scene_torch(h, w, sf, n, seed, device=f"cuda:{local}", j0=j0, j1=j1)
+        ctx = make_strip_context(sc["mask"], n, sf, sc["K"], rank, world, local, albedo_mode=args.albedo)
+    else:
+        # N independent replicas, one scene per GPU (BASELINE config 5 pattern, no communication)
+        sc = synth_scene_torch(h, w, sf, n, seed + rank, device=f"cuda:{local}")
+        ctx = Context(sc["mask"], n, sf, sc["K"], device=local, albedo_mode=args.albedo)
+    npix = ctx.npix                  # pixels this rank owns
     ctx.upload_state(sc["I"], sc["z"], sc["z0s"])
     torch.cuda.empty_cache()
 
@@ -274,14 +282,20 @@ def run_ours(args, rank, world, local):
         cb = cpu_baseline(args.cpu_sample, args.cpu_sample, sf, n, seed, npix)
     line = {
         "metric": METRIC if args.workload == "4k" else f"ms per outer iteration ({args.workload})",
-        "value": ms_step / world, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": False,
-        "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "value": ms_step if (strips or world == 1) else ms_step / world, "unit": "ms", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False,
+        "scaling": "strong" if (strips or world == 1) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{h}x{w} HR, sf={sf}, {n} images, full mask (BASELINE config {'4' if args.workload == '4k' else '3'})",
                    "albedo": args.albedo, "depth_cg": "reference schedule: un-preconditioned, 101 passes",
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas, one scene per GPU (value = ms per scene-iteration)",
-                   "l2": f"image stack {sc['I'].nbytes / 1e9:.2f} GB and CG working set {28 * npix / 1e6:.0f} MB per pass exceed the 126 MB L2: no flush needed"},
-        "e2e": {"value": e2e_ms / world, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "parallelism": "1 GPU" if world == 1 else (
+                       f"{world} strips of the same scene along the image columns, 1 ghost line per neighbour + 2 CG scalars per pass "
+                       f"exchanged in-kernel over NVLink peer memory" if strips else
+                       f"{world} independent replicas, one scene per GPU (value = ms per scene-iteration)"),
+                   "l2": (f"per GPU: image stack {sc['I'].nbytes / 1e9:.2f} GB, CG working set {28 * npix / 1e6:.0f} MB per pass; "
+                          + ("both exceed the 126 MB L2: no flush needed" if 28 * npix > 126e6 else
+                             "the stack exceeds the 126 MB L2, the CG vectors fit it (algorithmic GB/s of the CG may exceed the HBM peak)"))},
+        "e2e": {"value": e2e_ms if (strips or world == 1) else e2e_ms / world, "unit": "ms",
+                "h2d_bytes_per_step": h2d * (world if strips else 1), "d2h_bytes_per_step": d2h * (world if strips else 1),
                 "what": f"srps_upload_state (pinned host) + {args.steps} outer iterations + download of z, rho, N, s; total {e2e_ms_total:.1f} ms / {args.steps}"},
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -307,6 +321,8 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=1024, help="edge of the square sample the reference CUDA build is timed on")
     ap.add_argument("--ref-cpu", action="store_true", help="reference arm: use the CPU port instead of the reference CUDA build")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--parallelism", default="strips", choices=["strips", "replicas"],
+                    help="N > 1: strip-partition ONE scene (default, strong scaling) or run N independent scenes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, world, local = dist_setup(args.gpus)

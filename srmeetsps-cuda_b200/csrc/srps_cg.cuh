@@ -367,20 +367,23 @@ __global__ void __launch_bounds__(SW_NT, 3) stencil_strip_kernel(const StencilAr
         auto load_pn = [&](int j) -> float4 {
             if (!colok || j > ny) return f4zero();                // line ny is the zero guard line
             const long long off = (long long)j * pitch + x;
+            // read-only operands go through the non-coherent path (ld.global.nc): the compiler may then batch the
+            // loads of a whole group ahead of the stores of the previous lines (nothing read here is written here:
+            // the new p goes to the other ping-pong plane)
             if (MODE == MODE_ITER) {
-                const float4 r4 = ld4(a.r + off), p4 = ld4(a.p_in + off);
+                const float4 r4 = ldg4(a.r + off), p4 = ldg4(a.p_in + off);
                 return make_float4(r4.x + beta * p4.x, r4.y + beta * p4.y, r4.z + beta * p4.z, r4.w + beta * p4.w);
             }
-            return ld4(a.vin + off);
+            return ldg4(a.vin + off);
         };
         auto load_t = [&](int j) -> unsigned {
             if (!colok || j > ny) return 0u;
-            return ld_types(a.types, (long long)j * pitch + x);
+            return __ldg(reinterpret_cast<const unsigned*>(a.types + (long long)j * pitch + x));
         };
         auto load_w = [&](int j, float4& w0, float4& w1, float4& w2) {
             if (!colok || j > ny) { w0 = w1 = w2 = f4zero(); return; }
             const long long off = (long long)j * pitch + x;
-            w0 = ld4(a.w0 + off); w1 = ld4(a.w1 + off); w2 = ld4(a.w2 + off);
+            w0 = ldg4(a.w0 + off); w1 = ldg4(a.w1 + off); w2 = ldg4(a.w2 + off);
         };
 
         float4 pl[SW_G + 1], wl0[SW_G + 1], wl1[SW_G + 1], wl2[SW_G + 1];
@@ -404,7 +407,11 @@ __global__ void __launch_bounds__(SW_NT, 3) stencil_strip_kernel(const StencilAr
 #pragma unroll
             for (int l = 1; l <= SW_G; l++) {
                 pl[l] = load_pn(j0 + l); tl[l] = load_t(j0 + l); load_w(j0 + l, wl0[l], wl1[l], wl2[l]);
-                if (MODE == MODE_ITER && a.comm.world > 1 && j0 + l == ny && writer) st4(a.p_out + (long long)ny * pitch + x, pl[l]);
+            }
+            if (MODE == MODE_ITER && a.comm.world > 1 && j0 + SW_G >= ny && writer) {      // ghost line below: keep p there too
+#pragma unroll
+                for (int l = 1; l <= SW_G; l++)
+                    if (j0 + l == ny) st4(a.p_out + (long long)ny * pitch + x, pl[l]);
             }
             // sf x sf block sums of the group (the K of Kt K)
             float bs4 = 0.f, bs2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
@@ -489,6 +496,7 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_update_kernel(const UpdateArgs a)
     if (!a.sc->active) return;
     const float alpha = a.sc->alpha;
     double acc = 0.0;
+    bool pushed = false;
     const long long stride = (long long)gridDim.x * CG_NT;
     for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < a.n4; i += stride) {
         const float4 p4 = ld4(a.p + 4 * i), y4 = ld4(a.y + 4 * i);
@@ -498,13 +506,16 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_update_kernel(const UpdateArgs a)
         st4(a.x + 4 * i, x4);
         st4(a.r + 4 * i, r4);
         if (a.comm.world > 1) {        // push our first / last line of r into the neighbours' ghost lines (NVLink peer stores)
-            if (a.r_halo.prev_ghost && i < a.q_per_line) st4(a.r_halo.prev_ghost + 4 * i, r4);
-            if (a.r_halo.next_ghost && i >= a.n4 - a.q_per_line) st4(a.r_halo.next_ghost + 4 * (i - (a.n4 - a.q_per_line)), r4);
+            if (a.r_halo.prev_ghost && i < a.q_per_line) { st4(a.r_halo.prev_ghost + 4 * i, r4); pushed = true; }
+            if (a.r_halo.next_ghost && i >= a.n4 - a.q_per_line) { st4(a.r_halo.next_ghost + 4 * (i - (a.n4 - a.q_per_line)), r4); pushed = true; }
         }
         acc += (double)(r4.x * r4.x + r4.y * r4.y) + (double)(r4.z * r4.z + r4.w * r4.w);
     }
     double total;
-    if (grid_reduce_last_world<CG_NT>(acc, a.partials, a.ticket, red, total, a.comm)) {
+    // every thread of a block that pushed fences its own peer stores; thread 0's fence + the barrier inside the
+    // reduction then order them before the ticket
+    if (pushed) __threadfence_system();
+    if (grid_reduce_last_world<CG_NT>(acc, a.partials, a.ticket, red, total, a.comm, __syncthreads_or(pushed))) {
         if (threadIdx.x == 0) {
             CgScalars* s = a.sc;
             s->r0 = s->r1;

@@ -89,8 +89,8 @@ __device__ __forceinline__ void peer_allreduce(const PeerComm& c, double* vals, 
 // in `total` (all threads of that block).
 template <int NT>
 __device__ __forceinline__ bool grid_reduce_last_world(double v, double* partials, unsigned* ticket, double* red_smem,
-                                                       double& total, const PeerComm& c) {
-    if (!grid_reduce_last<NT>(v, partials, ticket, red_smem, total)) return false;
+                                                       double& total, const PeerComm& c, bool peer_stores = false) {
+    if (!grid_reduce_last<NT>(v, partials, ticket, red_smem, total, peer_stores)) return false;
     __shared__ double s_tot;
     if (threadIdx.x == 0) s_tot = total;
     __syncthreads();

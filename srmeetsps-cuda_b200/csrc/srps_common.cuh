@@ -83,7 +83,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // and is reset to 0 by the last block.
 template <int NT>
 __device__ __forceinline__ bool grid_reduce_last(double v, double* partials, unsigned* ticket, double* red_smem,
-                                                 double& total) {
+                                                 double& total, bool peer_stores = false) {
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     v = warp_sum(v);
@@ -94,7 +94,9 @@ __device__ __forceinline__ bool grid_reduce_last(double v, double* partials, uns
 #pragma unroll
         for (int i = 0; i < NT / 32; i++) b += red_smem[i];
         partials[blockIdx.x] = b;
-        __threadfence_system();       // also orders this block's halo stores into peer memory (srps_comm.cuh)
+        // a block that stored halo lines into PEER memory (srps_comm.cuh) needs the system-scope fence so that
+        // "mailbox flag seen" implies "halo arrived"; everybody else only needs device scope
+        if (peer_stores) __threadfence_system(); else __threadfence();
         unsigned t = atomicAdd(ticket, 1u);
         s_last = (t == gridDim.x - 1);
     }

@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(EP_NT) halo_push_kernel(const HaloPushArgs a) 
         const float* src = a.plane[pl] + (side ? (long long)(a.ny - 1) * a.pitch : 0);
         st4(dst + 4 * i, ld4(src + 4 * i));
     }
+    __threadfence_system();
     double total;
-    grid_reduce_last_world<EP_NT>(0.0, a.partials, a.ticket, red, total, a.comm);
+    grid_reduce_last_world<EP_NT>(0.0, a.partials, a.ticket, red, total, a.comm, true);
 }
 
 // masked vector -> dense plane (idx = dense offset of masked pixel p)
