@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(CG_NT, 3) stencil_kernel(const StencilArgs a) 
             const int it = tid + rep * CG_NT;
             const int ly = 1 + it / (TX / 4), q4 = it % (TX / 4);
             const int j = y0 + ly - 1, x = x0 + 4 * q4;
-            const bool ok = (j < ny) && (x < pitch);
+            // j == ny inside a partial tile: the zero guard line, or the ghost line of a strip partition whose
+            // backward x-rows reach line ny-1 -> its coefficients are loaded, its output is discarded in phase C
+            const bool ok = (j <= ny) && (x < pitch);
             const long long off = (long long)j * pitch + x;
             float4 w0 = f4zero(), w1 = f4zero(), w2 = f4zero(), gg0 = f4zero(), gg1 = f4zero(), gg2 = f4zero();
             if (ok) {

@@ -22,6 +22,7 @@ from srmeetsps_cuda_b200.dist import local_ranges, make_strip_context, strip_bou
 
 SCENES = [dict(h=96, w=128, sf=2, n=6, seed=7, mask_kind="ellipse"),
           dict(h=64, w=96, sf=2, n=6, seed=12, mask_kind="random95"),
+          dict(h=48, w=72, sf=2, n=6, seed=13, mask_kind="random95"),     # 36 lines per rank: ghost line inside a partial tile
           dict(h=300, w=64, sf=4, n=9, seed=9, mask_kind="full"),
           dict(h=40, w=48, sf=1, n=6, seed=5, mask_kind="random95")]
 
