@@ -1,0 +1,138 @@
+"""C++ host (src/host: reference-compatible SRPS class, DataHandlers, CLI) -- CPU parts: the loaders are
+bit-exact against the python/cv2 mirror of the reference loaders, the OpenCV-free init stays close to cv2's."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "src", "host", "srps_cli")
+
+
+@pytest.fixture(scope="module")
+def cli():
+    import srmeetsps_cuda_b200.build as b
+    b.build()
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "src", "host")], stdout=subprocess.DEVNULL)
+    return CLI
+
+
+def write_image_folder(root, h=48, w=64, sf=2, n=4, seed=0, dropout=0.0):
+    import cv2
+    rng = np.random.default_rng(seed)
+    os.makedirs(os.path.join(root, "RGB")); os.makedirs(os.path.join(root, "Depth"))
+    yy, xx = np.mgrid[0:h, 0:w]
+    mask = (((xx - w / 2) / (0.4 * w)) ** 2 + ((yy - h / 2) / (0.45 * h)) ** 2 < 1).astype(np.uint8) * 255
+    cv2.imwrite(os.path.join(root, "mask.png"), mask)
+    for i in range(n):
+        img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        cv2.imwrite(os.path.join(root, "RGB", f"img_{i:02d}.png"), img)
+    hs, ws = h // sf, w // sf
+    for i in range(3):
+        d = (30000 + 8000 * np.sin(np.arange(ws) / 7.0)[None, :] + 3000 * np.cos(np.arange(hs) / 5.0)[:, None]
+             + rng.integers(0, 200, size=(hs, ws))).astype(np.uint16)
+        if dropout > 0:
+            d[rng.random((hs, ws)) < dropout] = 0
+        cv2.imwrite(os.path.join(root, "Depth", f"d_{i:02d}.png"), d)
+    with open(os.path.join(root, "K.txt"), "w") as fh:
+        fh.write("80.5,0,31.5\n0,80.5,23.5\n0,0,1\n%d,0,9870" % sf)     # min_z = 0: a zero sample stays a zero depth
+    return root
+
+
+def run_init(cli, dstype, dsloc, out):
+    res = subprocess.run([cli, f"--dstype={dstype}", f"--dsloc={dsloc}", "--init-only", f"--dump-init={out}"],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    lines = res.stdout.splitlines()
+    assert lines[:2] == ["Small mask calculation", "Mean of depth values"] and lines[-1] == "Done!"   # SRPS.cu:106,119,337
+    from srmeetsps_cuda_b200.snapshot import read_snapshot
+    return read_snapshot(out)
+
+
+def python_init(folder):
+    from srmeetsps_cuda_b200 import ImageDataHandler, preprocess_depth
+    dh = ImageDataHandler().loadDataFromImages(folder)
+    h, w, sf = dh.I_h, dh.I_w, int(dh.sf)
+    mask = dh.mask != 0
+    zs, z_full = preprocess_depth(dh.z0, h, w, sf)
+    mflat = mask.ravel(order="F")
+    lr = mask.reshape(h // sf, sf, w // sf, sf).all(axis=(1, 3)).ravel(order="F")
+    I = dh.I.transpose(0, 1, 3, 2).reshape(dh.I_n, dh.I_c, h * w)[:, :, mflat]
+    return dh, I, z_full[mflat], zs[lr], mflat
+
+
+def test_cli_help_without_dsloc(cli):
+    res = subprocess.run([cli], capture_output=True, text=True)
+    assert res.returncode == 0 and "--dsloc" in res.stdout and "--dstype" in res.stdout      # Main.cpp:23-26
+
+
+def test_image_loader_and_init_match_python_mirror(cli, tmp_path):
+    folder = write_image_folder(str(tmp_path / "scene"))
+    snap = run_init(cli, "images", folder, str(tmp_path / "init.snap"))
+    dh, I, z, z0s, mflat = python_init(folder)
+    assert list(snap["dims"]) == [dh.I_h, dh.I_w, int(dh.sf)]
+    assert np.array_equal(snap["mask"].astype(bool), mflat)
+    assert np.array_equal(snap["K"], dh.K)
+    assert np.array_equal(snap["I"], I)                       # PNG decode + /255 + channel order: bit-exact
+    assert snap["z0s"].shape == z0s.shape and snap["z"].shape == z.shape
+    # no zero depth samples -> no inpainting: bilateral + bicubic only, cv2 uses a LUT for exp()
+    assert np.abs(snap["z0s"] - z0s).max() <= 2e-3 * np.abs(z0s).max()
+    assert np.abs(snap["z"] - z).max() <= 2e-3 * np.abs(z).max()
+
+
+def test_init_with_depth_dropout_stays_close_to_cv2(cli, tmp_path):
+    folder = write_image_folder(str(tmp_path / "scene"), dropout=0.02, seed=3)
+    snap = run_init(cli, "images", folder, str(tmp_path / "init.snap"))
+    dh, I, z, z0s, mflat = python_init(folder)
+    rel = np.abs(snap["z"] - z) / np.abs(z)
+    assert np.median(rel) < 2e-3 and rel.max() < 0.1          # Telea inpainting: not bit-identical to OpenCV
+
+
+def test_mat_loader(cli, tmp_path):
+    from scipy.io import savemat
+    folder = write_image_folder(str(tmp_path / "scene"))
+    from srmeetsps_cuda_b200 import ImageDataHandler
+    dh = ImageDataHandler().loadDataFromImages(folder)
+    for compress in (False, True):
+        path = str(tmp_path / f"scene_{int(compress)}.mat")
+        savemat(path, {"I": dh.I.transpose(2, 3, 1, 0).astype(np.float64), "K": dh.K.reshape(3, 3, order="F").astype(np.float64),
+                       "mask": (dh.mask != 0).astype(np.uint8), "sf": float(dh.sf), "z0": dh.z0.transpose(1, 2, 0).astype(np.float64)},
+                do_compression=compress)
+        a = run_init(cli, "matlab", path, str(tmp_path / "a.snap"))
+        b = run_init(cli, "images", folder, str(tmp_path / "b.snap"))
+        for k in ("dims", "mask", "K", "I", "z", "z0s"):
+            assert np.array_equal(a[k], b[k]), k
+    res = subprocess.run([cli, "--dstype=matlab", f"--dsloc={tmp_path}/missing.mat"], capture_output=True, text=True)
+    assert res.returncode != 0 and "Error opening MAT file" in res.stderr                    # Utilities.cpp:165-168
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/dataset/Images/Mitten"), reason="reference dataset not on this box")
+def test_mitten_loaders_bit_exact(cli, tmp_path):
+    snap = run_init(cli, "images", "/root/reference/dataset/Images/Mitten", str(tmp_path / "m.snap"))
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "mitten_init.npz"))
+    assert np.array_equal(snap["mask"], ref["mask"].ravel(order="F"))
+    assert np.array_equal(snap["I"], (ref["I8"].astype(np.float32) / np.float32(255)))
+    d = snap["z"] - ref["z"]
+    assert np.sqrt((d ** 2).mean()) < 0.2 and np.abs(d).max() < 5.0        # z in [535, 570]; OpenCV-free inpainting
+
+
+@pytest.mark.gpu
+def test_cli_loop_matches_python_host(cli, tmp_path, mitten_scene):
+    """The C++ SRPS::execute and the python Context drive the same library: identical energies."""
+    from srmeetsps_cuda_b200 import Context
+    from srmeetsps_cuda_b200.snapshot import read_snapshot, write_snapshot
+    sc = mitten_scene
+    snap_in = str(tmp_path / "mitten.snap")
+    write_snapshot(snap_in, {"dims": np.array([sc["h"], sc["w"], sc["sf"]], np.int32), "K": np.asarray(sc["K"], np.float32),
+                             "mask": (sc["mask"] != 0).astype(np.uint8).ravel(order="F"), "I": sc["I"], "z": sc["z"], "z0s": sc["z0s"]})
+    out = str(tmp_path / "res.snap")
+    res = subprocess.run([cli, "--dstype=snapshot", f"--dsloc={snap_in}", "--iters=3", f"--out={out}"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr + res.stdout
+    assert "Iteration 03 summary" in res.stdout and "Lightning Estimation" in res.stdout          # SRPS.cu:283,303
+    r = read_snapshot(out)
+    with Context(sc["mask"], sc["n"], sc["sf"], sc["K"]) as ctx:
+        ctx.upload_state(sc["I"], sc["z"], sc["z0s"])
+        e = [ctx.outer_iteration()[0] for _ in range(3)]
+        assert np.array_equal(np.asarray(e, np.float32), r["energy"])
+        assert np.array_equal(ctx.download("z"), r["z"])
