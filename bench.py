@@ -312,7 +312,7 @@ def run_ours(args, rank, world, local):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10, help="outer iterations timed (default 10 = the reference's MAX_ITERATIONS, SRPS.cu:86)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k", choices=list(WORKLOADS))
@@ -325,13 +325,17 @@ def main():
                     help="N > 1: strip-partition ONE scene (default, strong scaling) or run N independent scenes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
-    rank, world, local = dist_setup(args.gpus)
     if args.impl == "reference":
-        run_reference(args, rank, world)
-    else:
-        run_ours(args, rank, world, local)
+        # single-GPU program: under torchrun rank 0 alone runs it, the other ranks exit 0 without work
+        rank = int(os.environ.get("RANK", "0"))
+        if rank == 0:
+            run_reference(args, 0, 1)
+        return
+    rank, world, local = dist_setup(args.gpus)
+    run_ours(args, rank, world, local)
     if world > 1:
         import torch.distributed as dist
+        dist.barrier()
         dist.destroy_process_group()
 
 
