@@ -1,0 +1,107 @@
+"""Edge cases and error behaviour of the C ABI on a GPU."""
+import numpy as np
+import pytest
+
+from conftest import rel_rmse
+from oracle import srps_oracle as o
+from oracle.port import Port
+
+pytestmark = pytest.mark.gpu
+
+
+def test_call_order_errors():
+    from srmeetsps_cuda_b200 import Context, SRPSError
+    mask = np.ones((16, 16), np.uint8)
+    K = [20, 0, 0, 0, 20, 0, 7.5, 7.5, 1]
+    with Context(mask, 4, 2, K) as ctx:
+        with pytest.raises(SRPSError, match="no state uploaded"):
+            ctx.lighting()
+        with pytest.raises(SRPSError, match="no state uploaded"):
+            ctx.download("z")
+        rng = np.random.default_rng(0)
+        ctx.upload_state(rng.random((4, 3, ctx.npix), dtype=np.float32), np.full(ctx.npix, 500, np.float32),
+                         np.full(ctx.npixs, 500, np.float32))
+        with pytest.raises(SRPSError, match="needs srps_albedo first"):
+            ctx.depth()                      # closed-form mode forms the depth coefficients in the albedo pass
+        ctx.lighting(); ctx.albedo()
+        e, k = ctx.depth()
+        assert np.isfinite(e)
+
+
+def test_empty_mask_is_rejected():
+    from srmeetsps_cuda_b200 import Context, SRPSError
+    with pytest.raises(SRPSError, match="empty mask"):
+        Context(np.zeros((8, 8), np.uint8), 4, 2, [10, 0, 0, 0, 10, 0, 4, 4, 1])
+
+
+def test_single_pixel_islands_and_thin_lines():
+    """Pixels with no neighbour (empty Dx/Dy rows, SRPS.cu:31-46), 1-pixel-wide lines, a mask touching every image border."""
+    h, w, sf, n = 24, 32, 2, 6
+    sc = o.synth_scene(h, w, sf, n, seed=21, mask_kind="full")
+    mask = np.zeros((h, w), np.float32)
+    mask[0, :] = 1; mask[-1, :] = 1; mask[:, 0] = 1; mask[:, -1] = 1       # frame on the image border
+    mask[4:20, 10] = 1                                                     # vertical line
+    mask[12, 3:29] = 1                                                     # horizontal line
+    mask[6, 20] = 1; mask[18, 5] = 1                                       # isolated pixels
+    mask[14:20, 16:24] = 1                                                 # a block with LR support
+    ops = o.build_operators(mask, sf)
+    full = o.build_operators(np.ones((h, w), np.float32), sf)
+    sel = np.isin(full["imask"], ops["imask"])
+    lsel = np.isin(full["imasks"], ops["imasks"])
+    sc2 = dict(sc, mask=mask, ops=ops, I=np.ascontiguousarray(sc["I"][:, :, sel]), z=sc["z"][sel], z0s=sc["z0s"][lsel])
+    from srmeetsps_cuda_b200 import Context
+    st = o.init_state(sc2["I"], sc2["z"], sc2["z0s"], ops, sc2["K"], np.float32)
+    pt = Port(ops, n, 3, st["fx"], st["fy"], st["xx"], st["yy"])
+    stp = {k: np.ascontiguousarray(st[k]).copy() for k in ("s", "rho", "z", "N", "dz", "I", "z0s")}
+    for stencil in ("strip", "tile"):
+        import os
+        os.environ["SRPS_STENCIL"] = stencil
+        try:
+            with Context(mask, n, sf, sc2["K"]) as ctx:
+                assert ctx.npix == ops["npix"] and ctx.npixs == ops["npixs"]
+                ctx.upload_state(sc2["I"], sc2["z"], sc2["z0s"])
+                assert np.abs(ctx.download("N") - st["N"]).max() < 5e-6
+                ref = {k: v.copy() for k, v in stp.items()}
+                e_ref, k_ref, _ = pt.outer_iteration(ref, albedo_closed_form=True)
+                e, k = ctx.outer_iteration()
+                assert k == k_ref
+                assert rel_rmse(ctx.download("z"), ref["z"]) <= 1e-4
+                assert np.abs(ctx.download("rho") - ref["rho"]).max() <= 5e-3     # barely constrained pixels (no neighbours)
+        finally:
+            os.environ.pop("SRPS_STENCIL", None)
+
+
+def test_many_images_and_reupload():
+    """n = 64 (the shared-memory / mailbox limit) and re-uploading a second scene into the same context."""
+    from srmeetsps_cuda_b200 import Context
+    sc = o.synth_scene(32, 32, 4, 64, seed=2, mask_kind="ellipse")
+    st = o.init_state(sc["I"], sc["z"], sc["z0s"], sc["ops"], sc["K"], np.float32)
+    pt = Port(sc["ops"], sc["n"], sc["c"], st["fx"], st["fy"], st["xx"], st["yy"])
+    with Context(sc["mask"], 64, 4, sc["K"]) as ctx:
+        for rep in range(2):
+            ref = {k: np.ascontiguousarray(st[k]).copy() for k in ("s", "rho", "z", "N", "dz", "I", "z0s")}
+            ctx.upload_state(sc["I"], sc["z"], sc["z0s"])
+            for it in range(2):
+                e_ref, k_ref, _ = pt.outer_iteration(ref)
+                e, k = ctx.outer_iteration()
+                assert abs(k - k_ref) <= 1
+                assert rel_rmse(ctx.download("z"), ref["z"]) <= 1e-4
+                assert np.abs(ctx.download("rho") - ref["rho"]).max() <= 3e-3
+    from srmeetsps_cuda_b200 import SRPSError
+    with pytest.raises(SRPSError, match="n_images"):
+        Context(sc["mask"], 65, 4, sc["K"])
+
+
+def test_python_srps_class_runs_execute(tmp_path):
+    """The Python mirror of class SRPS (SRPS.h:10-18) end to end on a tiny image folder."""
+    import io
+    from test_cpp_host import write_image_folder
+    from srmeetsps_cuda_b200 import ImageDataHandler, SRPS
+    folder = write_image_folder(str(tmp_path / "scene"), h=48, w=64, sf=2, n=6, seed=4)
+    dh = ImageDataHandler().loadDataFromImages(folder)
+    out = io.StringIO()
+    s = SRPS(dh)
+    res = s.execute(out=out)
+    text = out.getvalue()
+    assert "Small mask calculation" in text and "Iteration 01 summary" in text and text.rstrip().endswith("Done!")
+    assert 1 <= len(s.history) <= 11 and np.isfinite(res["z"]).all() and res["N"].shape[0] == 4
