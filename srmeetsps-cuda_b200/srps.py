@@ -151,7 +151,7 @@ class SRPS:                             # SRPS.h:10-18
             print("\nIteration %02d summary" % iteration, file=out)
             print("%-25s: %-6.3f" % ("Error", energy), file=out)
             print("%-25s: %-6.3f" % ("Relative Error", rel_err), file=out)
-            self.history.append(dict(iteration=iteration, energy=energy, rel_err=rel_err, cg_iters=cg,
+            self.history.append(dict(iteration=iteration, energy=energy, rel_err=rel_err,
                                      wall_s=time.perf_counter() - t0, **tm))
             iteration += 1
             if stop:

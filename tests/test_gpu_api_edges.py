@@ -61,12 +61,26 @@ def test_single_pixel_islands_and_thin_lines():
                 assert ctx.npix == ops["npix"] and ctx.npixs == ops["npixs"]
                 ctx.upload_state(sc2["I"], sc2["z"], sc2["z0s"])
                 assert np.abs(ctx.download("N") - st["N"]).max() < 5e-6
+                # sharp check: the operator against the reference's assembled sparse system on this mask
+                rng = np.random.default_rng(1)
+                s_rand = (0.5 * rng.standard_normal((n, 3, 4))).astype(np.float32)
+                ctx.set_state("s", s_rand); ctx.albedo()
+                st64 = o.init_state(sc2["I"], sc2["z"], sc2["z0s"], ops, sc2["K"], np.float64)
+                _, _, _, mf = o.depth_update_matfree(s_rand.astype(np.float64), ctx.download("rho").astype(np.float64), st64["I"], st64["xx"],
+                                                     st64["yy"], ctx.download("dz").astype(np.float64), ops, st64["z0s"], st64["z"],
+                                                     st64["fx"], st64["fy"], np.float64)
+                p = rng.standard_normal(ctx.npix).astype(np.float32)
+                y_ref = mf["Aop"](p.astype(np.float64))
+                assert np.abs(ctx.apply_depth_operator(p) - y_ref).max() <= 2e-5 * np.abs(y_ref).max()
+                # one outer iteration: pixels on 1-pixel lines have no depth prior and a near-singular photometric
+                # term -> the 101-pass CG amplifies fp32 noise there, hence the looser tolerances
+                ctx.set_state("s", st["s"]); ctx.set_state("rho", st["rho"])
                 ref = {k: v.copy() for k, v in stp.items()}
                 e_ref, k_ref, _ = pt.outer_iteration(ref, albedo_closed_form=True)
                 e, k = ctx.outer_iteration()
                 assert k == k_ref
-                assert rel_rmse(ctx.download("z"), ref["z"]) <= 1e-4
-                assert np.abs(ctx.download("rho") - ref["rho"]).max() <= 5e-3     # barely constrained pixels (no neighbours)
+                assert rel_rmse(ctx.download("z"), ref["z"]) <= 5e-4
+                assert np.abs(ctx.download("rho") - ref["rho"]).max() <= 5e-3
         finally:
             os.environ.pop("SRPS_STENCIL", None)
 
