@@ -205,12 +205,15 @@ def run_ours(args, rank, world, local):
         # CG scalars travel inside the library's kernels over NVLink peer memory (csrc/srps_comm.cuh)
         j0, j1 = strip_bounds(w, world)[rank]
         sc = synth_scene_torch(h, w, sf, n, seed, device=f"cuda:{local}", j0=j0, j1=j1)
+        t_ctx = time.perf_counter()
         ctx = make_strip_context(sc["mask"], n, sf, sc["K"], rank, world, local, albedo_mode=args.albedo)
     else:
         # N independent replicas, one scene per GPU (BASELINE config 5 pattern, no communication)
         sc = synth_scene_torch(h, w, sf, n, seed + rank, device=f"cuda:{local}")
+        t_ctx = time.perf_counter()
         ctx = Context(sc["mask"], n, sf, sc["K"], device=local, albedo_mode=args.albedo)
     npix = ctx.npix                  # pixels this rank owns
+    t_ctx = (time.perf_counter() - t_ctx) * 1e3
     ctx.upload_state(sc["I"], sc["z"], sc["z0s"])
     torch.cuda.empty_cache()
 
@@ -305,6 +308,8 @@ def run_ours(args, rank, world, local):
         "cg_iters_per_s": float(np.mean(cg_iters)) / (float(np.mean(phases["ms_depth_cg"])) * 1e-3),
         "cg_iters": int(np.mean(cg_iters)),
         "energy_last": float(energies[-1]),
+        "one_shot_ms": {"ctx_create": t_ctx,
+                        "note": "mask analysis + allocation (the reference's one-shot init, SRPS.cu:151-203) is outside the per-iteration metric"},
     }
     print(json.dumps(line))
 

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsrps_b200.so")
+LIB_PATH = os.environ.get("SRPS_LIB") or os.path.join(HERE, "libsrps_b200.so")     # SRPS_LIB: A/B builds of the same ABI
 
 SRPS_ALBEDO_CLOSED_FORM = 0
 SRPS_ALBEDO_REFERENCE_CG = 1

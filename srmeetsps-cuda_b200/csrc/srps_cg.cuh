@@ -303,6 +303,10 @@ __global__ void __launch_bounds__(CG_NT, 3) stencil_kernel(const StencilArgs a) 
 // request; the only redundancy is the two halo lanes (6.7 % more L2->SM traffic, no extra DRAM
 // traffic) and one prologue line per chunk.
 // ---------------------------------------------------------------------------------------------
+#ifndef SRPS_STRIP_MINB
+#define SRPS_STRIP_MINB 3        // CTAs per SM the register allocation aims at: 3 -> <= 168 registers, no spills.
+#endif                           // Measured (round 1, 4096^2): 4 -> 128 registers with spills, 0.107 ms vs 0.092 ms; a register
+                                 // software pipeline (next group's r,p prefetched, w one line ahead) was 0.097 ms: both rejected.
 constexpr int SW_NT = 128;       // 4 independent warps per CTA
 constexpr int SW_COLS = 30;      // output float4 columns per warp
 constexpr int SW_G = 4;          // lines per group (multiple of sf)
@@ -339,7 +343,7 @@ __device__ __forceinline__ LineQ line_q(const LightConsts& lc, float fx, float f
 }
 
 template <int MODE, int SF>
-__global__ void __launch_bounds__(SW_NT, 3) stencil_strip_kernel(const StencilArgs a) {
+__global__ void __launch_bounds__(SW_NT, SRPS_STRIP_MINB) stencil_strip_kernel(const StencilArgs a) {
     static_assert(MODE == MODE_ITER || MODE == MODE_APPLY, "the warp-strip kernel implements ITER and APPLY");
     static_assert(SF == 1 || SF == 2 || SF == 4, "sf must divide the group height");
     __shared__ double red[SW_NT / 32];
