@@ -173,7 +173,7 @@ def run_reference(args, rank, world):
             scale = full_pixels / float(sh * sw)
             line.update({"value": ms * scale, "ms_per_step": ms * scale,
                          "config": {"workload": f"{h}x{w} sf={sf} n={n}", "sample": f"{sh}x{sw}", "scaled_by": scale},
-                         "cpu_baseline": {"value": ms * scale, "unit": "ms per outer iteration", "cores": 0, "kind": "reference",
+                         "cpu_baseline": {"value": ms * scale, "unit": "ms per outer iteration", "cores": 1, "kind": "reference",
                                           "sample": f"reference CUDA build (cuSPARSE/cuBLAS path on the GPU, no CPU path exists) on "
                                                     f"{sh}x{sw} sf={sf} n={n}: {ms:.1f} ms/iter measured, x{scale:g} per-pixel-linear "
                                                     f"extrapolation; it cannot run {h}x{w}x{n} (int32 nnz overflow, SURVEY F7)"},

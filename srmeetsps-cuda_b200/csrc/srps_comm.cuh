@@ -24,6 +24,7 @@ constexpr int MB_VALS = 800;      // doubles per (slot, source rank): lighting n
 
 struct Mailbox {
     unsigned long long flag[MB_SLOTS][MAX_RANKS];
+    unsigned long long ll[MB_SLOTS][MAX_RANKS][2];     // scalar fast path: {seq32 | low word}, {seq32 | high word}
     double val[MB_SLOTS][MAX_RANKS][MB_VALS];
 };
 
@@ -85,17 +86,47 @@ __device__ __forceinline__ void peer_allreduce(const PeerComm& c, double* vals, 
     __syncthreads();
 }
 
+// Scalar all-reduce, latency-optimised (the two per CG pass): the fp64 partial travels as two 8-byte words that
+// each carry the 32-bit sequence number next to 32 bits of payload, so data and flag arrive in ONE store (no
+// fence + flag round trip); 8-byte stores are single transactions.  st.release / ld.acquire at system scope
+// keep "word seen" => "the sender's earlier halo stores are visible".  Called by all threads of the last block;
+// returns the rank-ordered world total to every thread.
+template <int NT>
+__device__ __forceinline__ double peer_allreduce_scalar(const PeerComm& c, double v) {
+    if (c.world <= 1) return v;
+    __shared__ double s_part[MAX_RANKS];
+    __shared__ unsigned long long s_seq1;
+    if (threadIdx.x == 0) { s_seq1 = *c.seq + 1ull; s_part[0] = v; }
+    __syncthreads();
+    const unsigned long long seq = s_seq1;
+    const unsigned long long tag = (seq & 0xffffffffull) << 32;
+    const int slot = (int)(seq & (MB_SLOTS - 1));
+    const double mine = s_part[0];
+    __syncthreads();
+    if (threadIdx.x < c.world) {
+        const int t = threadIdx.x;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
+        st_release_sys(&c.peer[t]->ll[slot][c.rank][0], tag | (bits & 0xffffffffull));
+        st_release_sys(&c.peer[t]->ll[slot][c.rank][1], tag | (bits >> 32));
+        unsigned long long w0, w1;
+        do { w0 = ld_acquire_sys(&c.local->ll[slot][t][0]); } while ((w0 & 0xffffffff00000000ull) != tag);
+        do { w1 = ld_acquire_sys(&c.local->ll[slot][t][1]); } while ((w1 & 0xffffffff00000000ull) != tag);
+        s_part[t] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    }
+    __syncthreads();
+    double total = 0.0;
+    for (int r = 0; r < c.world; r++) total += s_part[r];      // rank order: identical bits on every rank
+    if (threadIdx.x == 0) *c.seq = seq;
+    return total;
+}
+
 // grid_reduce_last + the cross-rank sum: returns true in the last block of every rank with the WORLD total
 // in `total` (all threads of that block).
 template <int NT>
 __device__ __forceinline__ bool grid_reduce_last_world(double v, double* partials, unsigned* ticket, double* red_smem,
                                                        double& total, const PeerComm& c, bool peer_stores = false) {
     if (!grid_reduce_last<NT>(v, partials, ticket, red_smem, total, peer_stores)) return false;
-    __shared__ double s_tot;
-    if (threadIdx.x == 0) s_tot = total;
-    __syncthreads();
-    peer_allreduce<NT>(c, &s_tot, 1);
-    total = s_tot;
+    total = peer_allreduce_scalar<NT>(c, total);
     return true;
 }
 
