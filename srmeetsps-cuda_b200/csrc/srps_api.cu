@@ -60,6 +60,8 @@ struct srps_ctx {
     int grid_stencil = 0, grid_update = 0, grid_stack = 0, grid_light_x = 0, light_groups = 0, grid_ep = 0, grid_al = 0, grid_gram = 0;
     int tiles_x = 0, tiles_y = 0;
     int use_strip = 0, strip_n = 0, strip_chunks = 0, strip_cl = 0, grid_strip = 0;
+    int use_persistent = 0, grid_persistent = 0;      // all CG passes in one cooperative launch
+    unsigned long long* sync_words = nullptr;         // [0] grid barrier counter, [1] world generation, [2..5] world totals (as double)
     long long n4 = 0;
     cudaGraphExec_t cg_graph = nullptr;
     int use_graph = 1;
@@ -124,7 +126,7 @@ extern "C" void srps_ctx_destroy(srps_ctx* ctx) {
         if (ctx->peer_planes[r]) cudaIpcCloseMemHandle(ctx->peer_planes[r]);
         if (ctx->connected && r != ctx->rank && r < ctx->world && ctx->comm.peer[r]) cudaIpcCloseMemHandle(ctx->comm.peer[r]);
     }
-    cudaFree(ctx->mailbox); cudaFree(ctx->seq);
+    cudaFree(ctx->mailbox); cudaFree(ctx->seq); cudaFree(ctx->sync_words);
     cudaFree(ctx->plane_base); cudaFree(ctx->types_base); cudaFree(ctx->lrmask); cudaFree(ctx->idx); cudaFree(ctx->idx_lr);
     cudaFree(ctx->I_base); cudaFree(ctx->z0lr); cudaFree(ctx->s); cudaFree(ctx->gram); cudaFree(ctx->lc); cudaFree(ctx->sc);
     cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->energy); cudaFree(ctx->staging); cudaFree(ctx->U);
@@ -313,6 +315,20 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         ctx->strip_chunks = (g.ny + cl - 1) / cl;
         const int nitems = ctx->strip_n * ctx->strip_chunks;
         ctx->grid_strip = std::min((nitems + SW_NT / 32 - 1) / (SW_NT / 32), ctx->sm_count * std::max(1, occ));
+        // persistent CG (one cooperative launch per solve): every block must be resident at once
+        int coop = 0, occ_p = 0;
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, cg_persistent_kernel<4>, SW_NT, 0));
+        const char* cgm = getenv("SRPS_CG");
+        // Measured (round 1): the persistent form wins on small single-GPU scenes (Mitten 1.41 vs 1.52 ms, 1080p 2.74 vs
+        // 2.95 ms per outer iteration: fewer, cheaper synchronisation points), loses at 4096^2 (its update phase runs on the
+        // operator's 128-thread blocks: 17.7 vs 15.4 ms) and does not help the strip partition (2 GPUs: 11.9 vs 10.2 ms).
+        // Default: persistent below 3 M pixels on one GPU; SRPS_CG=persistent|graph overrides.
+        const bool want = cgm ? strcmp(cgm, "persistent") == 0 : (ctx->world == 1 && npix < 3000000);
+        ctx->use_persistent = ctx->use_strip && coop && occ_p > 0 && want;
+        ctx->grid_persistent = std::min(ctx->grid_strip, ctx->sm_count * std::max(1, occ_p));
+        CK(cudaMalloc(&ctx->sync_words, 8 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(ctx->sync_words, 0, 8 * sizeof(unsigned long long), ctx->stream));
     }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_update_kernel, CG_NT, 0));
     ctx->grid_update = (int)std::min<long long>((ctx->n4 + CG_NT - 1) / CG_NT, (long long)ctx->sm_count * std::max(1, occ));
@@ -718,7 +734,19 @@ extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
     ua.comm = ctx->comm; ua.r_halo = halo_peers(ctx, ctx->r); ua.q_per_line = ctx->g.pitch / 4;
     const int passes = ctx->h_sc[0].max_iter + 1;     // k <= max_iter -> max_iter + 1 passes   devicecalls.cu:252
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
-    if (getenv("SRPS_TRACE")) {
+    if (ctx->use_persistent && !getenv("SRPS_TRACE")) {
+        PersistentArgs pa{};
+        pa.st = sa; pa.pp[0] = ctx->p; pa.pp[1] = ctx->p2; pa.x = ctx->z; pa.r = ctx->r; pa.n4 = ctx->n4;
+        pa.q_per_line = ctx->g.pitch / 4; pa.r_halo = halo_peers(ctx, ctx->r); pa.passes = passes;
+        pa.bar = ctx->sync_words; pa.world_gen = ctx->sync_words + 1; pa.world_tot = (double*)(ctx->sync_words + 2);
+        pa.part[0] = ctx->partials; pa.part[1] = ctx->partials + ctx->grid_persistent;
+        CK(cudaMemsetAsync(ctx->sync_words, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        void* kargs[] = {&pa};
+        const void* fn = ctx->g.sf == 1 ? (const void*)cg_persistent_kernel<1>
+                         : (ctx->g.sf == 2 ? (const void*)cg_persistent_kernel<2> : (const void*)cg_persistent_kernel<4>);
+        CK(cudaLaunchCooperativeKernel(fn, dim3(ctx->grid_persistent), dim3(SW_NT), kargs, 0, ctx->stream));
+        ctx->launches++;
+    } else if (getenv("SRPS_TRACE")) {
         // debugging aid: one pass at a time, CG scalars printed after each (no graph)
         for (int k = 0; k < passes; k++) {
             StencilArgs s1 = sa; UpdateArgs u1 = ua;

@@ -342,18 +342,13 @@ __device__ __forceinline__ LineQ line_q(const LightConsts& lc, float fx, float f
     return o;
 }
 
+// One application of the operator over this block's share of the (strip, chunk) items.  `a.p_in` / `a.p_out`
+// are the ping-pong planes of this pass; returns this thread's partial of p.y (MODE_ITER).
 template <int MODE, int SF>
-__global__ void __launch_bounds__(SW_NT, SRPS_STRIP_MINB) stencil_strip_kernel(const StencilArgs a) {
+__device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightConsts& lc, float beta) {
     static_assert(MODE == MODE_ITER || MODE == MODE_APPLY, "the warp-strip kernel implements ITER and APPLY");
     static_assert(SF == 1 || SF == 2 || SF == 4, "sf must divide the group height");
-    __shared__ double red[SW_NT / 32];
     const Grid& g = a.g;
-    float beta = 0.f;
-    if (MODE == MODE_ITER) {
-        if (!a.sc->active) return;
-        beta = a.sc->beta;
-    }
-    const LightConsts lc = *a.lc;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pitch = g.pitch, ny = g.ny;
     const float inv4 = 1.f / (float)(SF * SF * SF * SF);
@@ -475,6 +470,19 @@ __global__ void __launch_bounds__(SW_NT, SRPS_STRIP_MINB) stencil_strip_kernel(c
         }
     }
 
+    return dot;
+}
+
+template <int MODE, int SF>
+__global__ void __launch_bounds__(SW_NT, SRPS_STRIP_MINB) stencil_strip_kernel(const StencilArgs a) {
+    __shared__ double red[SW_NT / 32];
+    float beta = 0.f;
+    if (MODE == MODE_ITER) {
+        if (!a.sc->active) return;
+        beta = a.sc->beta;
+    }
+    const LightConsts lc = *a.lc;
+    const double dot = strip_pass<MODE, SF>(a, lc, beta);
     if (MODE == MODE_APPLY) return;
     double total;
     if (grid_reduce_last_world<SW_NT>(dot, a.partials, a.ticket, red, total, a.comm)) {
@@ -530,6 +538,139 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_update_kernel(const UpdateArgs a)
             s->beta = (float)total / (float)s->r0;                                  // devicecalls.cu:262
             s->active = ((float)total > s->tol2) && (s->k <= s->max_iter);          // devicecalls.cu:252
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent CG: ALL passes of one depth solve in ONE cooperative launch (sf <= 4).
+//
+// The two-kernel form pays, per pass, two launches and two "last block" reductions (~10-14 us): that is the
+// whole cost of a pass on small scenes (Mitten: 148 600 pixels) and the scaling limit of the strip partition.
+// Here every resident CTA runs  operator -> grid barrier -> update -> grid barrier  101 times.  The barrier is a
+// monotonic counter in global memory; each block publishes its fp64 partial before arriving and, after the
+// barrier, EVERY block sums all partials in the same fixed order, so all blocks hold bit-identical alpha / beta /
+// active without a broadcast.  With a strip partition, block 0 additionally all-reduces the rank total with the
+// peers (peer_allreduce_scalar) and publishes the world total to the other blocks through a generation-tagged slot.
+// The CG recurrences are those of devicecalls.cu:252-275, as in the two-kernel form.
+// ---------------------------------------------------------------------------------------------
+struct PersistentArgs {
+    StencilArgs st;                 // operator operands (p_in / p_out are set per pass)
+    float* pp[2];                   // the two ping-pong planes of the search direction: pass k reads pp[k&1], writes pp[(k+1)&1]
+    float* x;                       // z
+    float* r;                       // residual (read + written)
+    long long n4;
+    int q_per_line;
+    HaloPeers r_halo;
+    int passes;                     // max_iter + 1
+    unsigned long long* bar;        // grid barrier counter, zero on entry
+    double* part[2];                // per-block partials of the two reductions of a pass, gridDim.x doubles each
+    double* world_tot;              // [4] world totals published by block 0 (strip partition)
+    unsigned long long* world_gen;  // generation of the last published world total
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// publish `v`, wait for every block, return the (world) total -- identical bits in every thread of every block
+__device__ __forceinline__ double grid_allreduce(const PersistentArgs& a, double v, int which, unsigned long long& gen,
+                                                 double* red_smem, bool peer_stores) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ double s_total;
+    v = warp_sum(v);
+    if (lane == 0) red_smem[wid] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double b = 0.0;
+#pragma unroll
+        for (int i = 0; i < SW_NT / 32; i++) b += red_smem[i];
+        a.part[which][blockIdx.x] = b;
+        if (peer_stores) __threadfence_system(); else __threadfence();
+        atomicAdd(a.bar, 1ull);
+        const unsigned long long target = (gen + 1ull) * gridDim.x;
+        while (ld_acquire_gpu(a.bar) < target) { }
+    }
+    __syncthreads();
+    gen += 1ull;
+    if (wid == 0) {       // fixed summation order: lane-strided partials, then the xor tree
+        double t = 0.0;
+        for (int i = lane; i < (int)gridDim.x; i += 32) t += __ldcg(a.part[which] + i);
+        t = warp_sum(t);
+        if (lane == 0) s_total = t;
+    }
+    __syncthreads();
+    double total = s_total;
+    if (a.st.comm.world > 1) {
+        // one block talks to the peers; the others pick the world total up from a generation-tagged slot
+        if (blockIdx.x == 0) {
+            total = peer_allreduce_scalar<SW_NT>(a.st.comm, total);
+            if (threadIdx.x == 0) {
+                a.world_tot[gen & 3ull] = total;
+                __threadfence();
+                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.world_gen), "l"(gen) : "memory");
+            }
+        } else {
+            if (threadIdx.x == 0) {
+                while (ld_acquire_gpu(a.world_gen) < gen) { }
+                s_total = __ldcg(a.world_tot + (gen & 3ull));
+            }
+            __syncthreads();
+            total = s_total;
+        }
+    }
+    __syncthreads();
+    return total;
+}
+
+template <int SF>
+__global__ void __launch_bounds__(SW_NT, SRPS_STRIP_MINB) cg_persistent_kernel(const PersistentArgs a) {
+    __shared__ double red[SW_NT / 32];
+    CgScalars* sc = a.st.sc;
+    if (!sc->active) return;                         // r.r <= tol^2 already after the residual kernel (uniform)
+    const LightConsts lc = *a.st.lc;
+    double r1 = sc->r1, r0 = 0.0;
+    const float tol2 = sc->tol2;
+    const int max_iter = sc->max_iter;
+    float beta = 0.f;
+    int k = 0;
+    unsigned long long gen = 0ull;
+    StencilArgs st = a.st;
+    const long long stride = (long long)gridDim.x * SW_NT;
+    for (int pass = 0; pass < a.passes; pass++) {
+        // ---- p <- r + beta p ; y <- A p ; p.y                         devicecalls.cu:256-268
+        st.p_in = a.pp[pass & 1];
+        st.p_out = a.pp[(pass + 1) & 1];
+        const double dot = grid_allreduce(a, strip_pass<MODE_ITER, SF>(st, lc, beta), 0, gen, red, false);
+        const float alpha = (float)r1 / (float)dot;                      // devicecalls.cu:269
+        // ---- x += alpha p ; r -= alpha y ; r.r                          devicecalls.cu:270-274
+        double acc = 0.0;
+        bool pushed = false;
+        const float* pn = st.p_out;
+        for (long long i = (long long)blockIdx.x * SW_NT + threadIdx.x; i < a.n4; i += stride) {
+            const float4 p4 = ld4(pn + 4 * i), y4 = ld4(st.y + 4 * i);
+            float4 x4 = ld4(a.x + 4 * i), r4 = ld4(a.r + 4 * i);
+            x4.x += alpha * p4.x; x4.y += alpha * p4.y; x4.z += alpha * p4.z; x4.w += alpha * p4.w;
+            r4.x -= alpha * y4.x; r4.y -= alpha * y4.y; r4.z -= alpha * y4.z; r4.w -= alpha * y4.w;
+            st4(a.x + 4 * i, x4);
+            st4(a.r + 4 * i, r4);
+            if (st.comm.world > 1) {
+                if (a.r_halo.prev_ghost && i < a.q_per_line) { st4(a.r_halo.prev_ghost + 4 * i, r4); pushed = true; }
+                if (a.r_halo.next_ghost && i >= a.n4 - a.q_per_line) { st4(a.r_halo.next_ghost + 4 * (i - (a.n4 - a.q_per_line)), r4); pushed = true; }
+            }
+            acc += (double)(r4.x * r4.x + r4.y * r4.y) + (double)(r4.z * r4.z + r4.w * r4.w);
+        }
+        if (pushed) __threadfence_system();
+        const bool any_pushed = __syncthreads_or(pushed);
+        const double rr = grid_allreduce(a, acc, 1, gen, red, any_pushed);
+        r0 = r1; r1 = rr; k++;
+        beta = (float)r1 / (float)r0;                                    // devicecalls.cu:262
+        if (!(((float)r1 > tol2) && (k <= max_iter))) break;             // devicecalls.cu:252
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->r1 = r1; sc->r0 = r0; sc->k = k; sc->beta = beta;
+        sc->active = ((float)r1 > tol2) && (k <= max_iter);
     }
 }
 
