@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_update_kernel(const UpdateArgs a)
     // every thread of a block that pushed fences its own peer stores; thread 0's fence + the barrier inside the
     // reduction then order them before the ticket
     if (pushed) __threadfence_system();
-    if (grid_reduce_last_world<CG_NT>(acc, a.partials, a.ticket, red, total, a.comm, __syncthreads_or(pushed))) {
+    if (grid_reduce_last_world<CG_NT>(acc, a.partials, a.ticket, red, total, a.comm, __syncthreads_or(pushed), a.comm.world > 1)) {
         if (threadIdx.x == 0) {
             CgScalars* s = a.sc;
             s->r0 = s->r1;
@@ -605,7 +605,7 @@ __device__ __forceinline__ double grid_allreduce(const PersistentArgs& a, double
     if (a.st.comm.world > 1) {
         // one block talks to the peers; the others pick the world total up from a generation-tagged slot
         if (blockIdx.x == 0) {
-            total = peer_allreduce_scalar<SW_NT>(a.st.comm, total);
+            total = peer_allreduce_scalar<SW_NT>(a.st.comm, total, which == 1);
             if (threadIdx.x == 0) {
                 a.world_tot[gen & 3ull] = total;
                 __threadfence();

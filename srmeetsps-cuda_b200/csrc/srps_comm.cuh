@@ -43,6 +43,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
     asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
@@ -92,7 +100,7 @@ __device__ __forceinline__ void peer_allreduce(const PeerComm& c, double* vals, 
 // keep "word seen" => "the sender's earlier halo stores are visible".  Called by all threads of the last block;
 // returns the rank-ordered world total to every thread.
 template <int NT>
-__device__ __forceinline__ double peer_allreduce_scalar(const PeerComm& c, double v) {
+__device__ __forceinline__ double peer_allreduce_scalar(const PeerComm& c, double v, bool release) {
     if (c.world <= 1) return v;
     __shared__ double s_part[MAX_RANKS];
     __shared__ unsigned long long s_seq1;
@@ -106,14 +114,18 @@ __device__ __forceinline__ double peer_allreduce_scalar(const PeerComm& c, doubl
     if (threadIdx.x < c.world) {
         const int t = threadIdx.x;
         const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
-        st_release_sys(&c.peer[t]->ll[slot][c.rank][0], tag | (bits & 0xffffffffull));
-        st_release_sys(&c.peer[t]->ll[slot][c.rank][1], tag | (bits >> 32));
+        // `release`: halo lines were stored into peer memory by this kernel (by blocks that fenced them before taking
+        // their reduction ticket): ONE system fence orders them before the words below.  The words themselves are
+        // self-validating (sequence tag inside), so no second fence / flag round trip is needed.
+        if (release) __threadfence_system();
+        st_relaxed_sys_u64(&c.peer[t]->ll[slot][c.rank][0], tag | (bits & 0xffffffffull));
+        st_relaxed_sys_u64(&c.peer[t]->ll[slot][c.rank][1], tag | (bits >> 32));
         unsigned long long w0, w1;
-        do { w0 = ld_acquire_sys(&c.local->ll[slot][t][0]); } while ((w0 & 0xffffffff00000000ull) != tag);
-        do { w1 = ld_acquire_sys(&c.local->ll[slot][t][1]); } while ((w1 & 0xffffffff00000000ull) != tag);
+        do { w0 = ld_relaxed_sys_u64(&c.local->ll[slot][t][0]); } while ((w0 & 0xffffffff00000000ull) != tag);
+        do { w1 = ld_relaxed_sys_u64(&c.local->ll[slot][t][1]); } while ((w1 & 0xffffffff00000000ull) != tag);
         s_part[t] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
     }
-    __syncthreads();
+    __syncthreads();        // ghost lines are read by the NEXT kernel: the kernel boundary is the acquire
     double total = 0.0;
     for (int r = 0; r < c.world; r++) total += s_part[r];      // rank order: identical bits on every rank
     if (threadIdx.x == 0) *c.seq = seq;
@@ -124,9 +136,12 @@ __device__ __forceinline__ double peer_allreduce_scalar(const PeerComm& c, doubl
 // in `total` (all threads of that block).
 template <int NT>
 __device__ __forceinline__ bool grid_reduce_last_world(double v, double* partials, unsigned* ticket, double* red_smem,
-                                                       double& total, const PeerComm& c, bool peer_stores = false) {
-    if (!grid_reduce_last<NT>(v, partials, ticket, red_smem, total, peer_stores)) return false;
-    total = peer_allreduce_scalar<NT>(c, total);
+                                                       double& total, const PeerComm& c, bool block_pushed = false,
+                                                       bool kernel_pushes = false) {
+    // block_pushed: THIS block stored halo lines into peer memory (system fence before its ticket);
+    // kernel_pushes: some block of this kernel did (the last block releases at system scope before the mailbox words)
+    if (!grid_reduce_last<NT>(v, partials, ticket, red_smem, total, block_pushed)) return false;
+    total = peer_allreduce_scalar<NT>(c, total, kernel_pushes);
     return true;
 }
 

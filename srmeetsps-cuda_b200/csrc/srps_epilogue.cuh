@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(EP_NT) halo_push_kernel(const HaloPushArgs a) 
     }
     __threadfence_system();
     double total;
-    grid_reduce_last_world<EP_NT>(0.0, a.partials, a.ticket, red, total, a.comm, true);
+    grid_reduce_last_world<EP_NT>(0.0, a.partials, a.ticket, red, total, a.comm, true, true);
 }
 
 // masked vector -> dense plane (idx = dense offset of masked pixel p)
