@@ -324,7 +324,7 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         // 2.95 ms per outer iteration: fewer, cheaper synchronisation points), loses at 4096^2 (its update phase runs on the
         // operator's 128-thread blocks: 17.7 vs 15.4 ms) and does not help the strip partition (2 GPUs: 11.9 vs 10.2 ms).
         // Default: persistent below 3 M pixels on one GPU; SRPS_CG=persistent|graph overrides.
-        const bool want = cgm ? strcmp(cgm, "persistent") == 0 : (ctx->world == 1 && npix < 3000000);
+        const bool want = ctx->world == 1 && (cgm ? strcmp(cgm, "persistent") == 0 : npix < 3000000);
         ctx->use_persistent = ctx->use_strip && coop && occ_p > 0 && want;
         ctx->grid_persistent = std::min(ctx->grid_strip, ctx->sm_count * std::max(1, occ_p));
         CK(cudaMalloc(&ctx->sync_words, 8 * sizeof(unsigned long long)));
@@ -644,6 +644,19 @@ static void fill_stencil_args(srps_ctx* ctx, StencilArgs& sa) {
     sa.tiles_x = ctx->tiles_x; sa.tiles_y = ctx->tiles_y;
     sa.strip_n = ctx->strip_n; sa.strip_chunks = ctx->strip_chunks; sa.strip_cl = ctx->strip_cl;
     sa.comm = ctx->comm;
+    sa.r_prev_line = nullptr; sa.r_next_line = nullptr;
+    if (ctx->connected) {       // the neighbours' boundary lines of r, read in place over NVLink
+        const Grid& g = ctx->g;
+        const long long k = (ctx->r - g.origin() - ctx->plane_base) / g.plane;
+        if (ctx->rank > 0) {
+            const int q = ctx->rank - 1;
+            sa.r_prev_line = (const float*)ctx->peer_planes[q] + k * ctx->peer_plane[q] + g.origin() + (long long)(ctx->peer_ny[q] - 1) * g.pitch;
+        }
+        if (ctx->rank + 1 < ctx->world) {
+            const int q = ctx->rank + 1;
+            sa.r_next_line = (const float*)ctx->peer_planes[q] + k * ctx->peer_plane[q] + g.origin();
+        }
+    }
 }
 
 // Ghost-line addresses of plane `local_plane` inside the two neighbours' (mapped) plane allocations.
@@ -727,17 +740,18 @@ extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
     si.y = ctx->r;
     LAUNCH(ctx, stencil_kernel<MODE_INIT>, ctx->grid_stencil, CG_NT, si);
     CK(cudaGetLastError());
-    if ((rc = halo_push(ctx, {ctx->r}))) return rc;
+    // (the ghost lines of r are pulled from the neighbours inside the operator kernel: no push here; the r.r all-reduce
+    //  at the end of the residual kernel orders the neighbours' writes before the first pass)
     UpdateArgs ua{};
     ua.x = ctx->z; ua.r = ctx->r; ua.p = ctx->p; ua.y = ctx->y; ua.n4 = ctx->n4; ua.sc = ctx->sc; ua.partials = ctx->partials;
     ua.ticket = ctx->tickets + 5;
-    ua.comm = ctx->comm; ua.r_halo = halo_peers(ctx, ctx->r); ua.q_per_line = ctx->g.pitch / 4;
+    ua.comm = ctx->comm;
     const int passes = ctx->h_sc[0].max_iter + 1;     // k <= max_iter -> max_iter + 1 passes   devicecalls.cu:252
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     if (ctx->use_persistent && !getenv("SRPS_TRACE")) {
         PersistentArgs pa{};
         pa.st = sa; pa.pp[0] = ctx->p; pa.pp[1] = ctx->p2; pa.x = ctx->z; pa.r = ctx->r; pa.n4 = ctx->n4;
-        pa.q_per_line = ctx->g.pitch / 4; pa.r_halo = halo_peers(ctx, ctx->r); pa.passes = passes;
+        pa.passes = passes;
         pa.bar = ctx->sync_words; pa.world_gen = ctx->sync_words + 1; pa.world_tot = (double*)(ctx->sync_words + 2);
         pa.part[0] = ctx->partials; pa.part[1] = ctx->partials + ctx->grid_persistent;
         CK(cudaMemsetAsync(ctx->sync_words, 0, 2 * sizeof(unsigned long long), ctx->stream));
@@ -922,7 +936,7 @@ extern "C" int srps_profile_kernels(srps_ctx* ctx, int reps, float* out_ms) {
     UpdateArgs ua{};
     ua.x = ctx->y; ua.r = ctx->r; ua.p = ctx->p; ua.y = ctx->p2; ua.n4 = ctx->n4; ua.sc = ctx->sc; ua.partials = ctx->partials;
     ua.ticket = ctx->tickets + 5;
-    ua.comm = ctx->comm; ua.r_halo = halo_peers(ctx, ctx->r); ua.q_per_line = ctx->g.pitch / 4;
+    ua.comm = ctx->comm;
     // warm-up + stencil alone
     for (int pass = 0; pass < 2; pass++) {
         if (pass == 1) CK(cudaEventRecord(e0, ctx->stream));

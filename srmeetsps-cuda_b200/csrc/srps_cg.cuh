@@ -45,6 +45,11 @@ struct StencilArgs {
     int tiles_x, tiles_y;
     int strip_n, strip_chunks, strip_cl;   // warp-strip kernel: strips per line, chunks per strip, lines per chunk
     PeerComm comm;                         // world == 1: single GPU
+    // strip partition: the residual on the two ghost lines is PULLED from the neighbours' boundary lines (mapped peer
+    // pointers; nullptr at the ends of the image).  The r.r all-reduce that ends every update kernel guarantees that the
+    // neighbour finished writing r before this pass starts, so no halo push and no system-scope fence is needed.
+    const float* r_prev_line;              // previous rank's line ny_prev-1 of r
+    const float* r_next_line;              // next rank's line 0 of r
 };
 
 struct StencilSmem {
@@ -365,26 +370,36 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
         const int jB = min(jA + a.strip_cl, ny);
         const float yy0 = (float)(g.ib0 + x) - g.cy;
 
+        // Loads are UNCONDITIONAL with a clamped address (the plane origin is always valid) and a select on the result:
+        // no branch regions, so the ~24 loads of a group are issued back to back.  Read-only operands use the
+        // non-coherent path (nothing read here is written here: the new p goes to the other ping-pong plane).
+        // Strip partition: r on a ghost line (j = -1 / ny) is read in place from the neighbour's boundary line over
+        // NVLink (pointer select).  Peer lines may sit in this SM's L1 only within one launch; every pass is its own
+        // launch (the single-launch persistent CG is not used with a strip partition).
+        auto zsel = [](float4 v, bool ok) -> float4 {
+            return make_float4(ok ? v.x : 0.f, ok ? v.y : 0.f, ok ? v.z : 0.f, ok ? v.w : 0.f);
+        };
         auto load_pn = [&](int j) -> float4 {
-            if (!colok || j > ny) return f4zero();                // line ny is the zero guard line
-            const long long off = (long long)j * pitch + x;
-            // read-only operands go through the non-coherent path (ld.global.nc): the compiler may then batch the
-            // loads of a whole group ahead of the stores of the previous lines (nothing read here is written here:
-            // the new p goes to the other ping-pong plane)
+            const bool ok = colok && j <= ny;                      // line ny is the zero guard (or ghost) line
+            const long long off = ok ? (long long)j * pitch + x : 0;
             if (MODE == MODE_ITER) {
-                const float4 r4 = ldg4(a.r + off), p4 = ldg4(a.p_in + off);
-                return make_float4(r4.x + beta * p4.x, r4.y + beta * p4.y, r4.z + beta * p4.z, r4.w + beta * p4.w);
+                const float* rs = a.r + off;
+                rs = (ok && j < 0 && a.r_prev_line) ? a.r_prev_line + x : rs;
+                rs = (ok && j == ny && a.r_next_line) ? a.r_next_line + x : rs;
+                const float4 r4 = ldg4(rs), p4 = ldg4(a.p_in + off);
+                return zsel(make_float4(r4.x + beta * p4.x, r4.y + beta * p4.y, r4.z + beta * p4.z, r4.w + beta * p4.w), ok);
             }
-            return ldg4(a.vin + off);
+            return zsel(ldg4(a.vin + off), ok);
         };
         auto load_t = [&](int j) -> unsigned {
-            if (!colok || j > ny) return 0u;
-            return __ldg(reinterpret_cast<const unsigned*>(a.types + (long long)j * pitch + x));
+            const bool ok = colok && j <= ny;
+            const unsigned t = __ldg(reinterpret_cast<const unsigned*>(a.types + (ok ? (long long)j * pitch + x : 0)));
+            return ok ? t : 0u;
         };
         auto load_w = [&](int j, float4& w0, float4& w1, float4& w2) {
-            if (!colok || j > ny) { w0 = w1 = w2 = f4zero(); return; }
-            const long long off = (long long)j * pitch + x;
-            w0 = ldg4(a.w0 + off); w1 = ldg4(a.w1 + off); w2 = ldg4(a.w2 + off);
+            const bool ok = colok && j <= ny;
+            const long long off = ok ? (long long)j * pitch + x : 0;
+            w0 = zsel(ldg4(a.w0 + off), ok); w1 = zsel(ldg4(a.w1 + off), ok); w2 = zsel(ldg4(a.w2 + off), ok);
         };
 
         float4 pl[SW_G + 1], wl0[SW_G + 1], wl1[SW_G + 1], wl2[SW_G + 1];
@@ -501,8 +516,6 @@ struct UpdateArgs {
     double* partials;
     unsigned* ticket;
     PeerComm comm;
-    HaloPeers r_halo;          // strip partition: where the neighbours keep our boundary lines of r
-    int q_per_line;
 };
 
 __global__ void __launch_bounds__(CG_NT, 4) cg_update_kernel(const UpdateArgs a) {
@@ -510,7 +523,6 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_update_kernel(const UpdateArgs a)
     if (!a.sc->active) return;
     const float alpha = a.sc->alpha;
     double acc = 0.0;
-    bool pushed = false;
     const long long stride = (long long)gridDim.x * CG_NT;
     for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < a.n4; i += stride) {
         const float4 p4 = ld4(a.p + 4 * i), y4 = ld4(a.y + 4 * i);
@@ -519,17 +531,10 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_update_kernel(const UpdateArgs a)
         r4.x -= alpha * y4.x; r4.y -= alpha * y4.y; r4.z -= alpha * y4.z; r4.w -= alpha * y4.w;
         st4(a.x + 4 * i, x4);
         st4(a.r + 4 * i, r4);
-        if (a.comm.world > 1) {        // push our first / last line of r into the neighbours' ghost lines (NVLink peer stores)
-            if (a.r_halo.prev_ghost && i < a.q_per_line) { st4(a.r_halo.prev_ghost + 4 * i, r4); pushed = true; }
-            if (a.r_halo.next_ghost && i >= a.n4 - a.q_per_line) { st4(a.r_halo.next_ghost + 4 * (i - (a.n4 - a.q_per_line)), r4); pushed = true; }
-        }
         acc += (double)(r4.x * r4.x + r4.y * r4.y) + (double)(r4.z * r4.z + r4.w * r4.w);
     }
     double total;
-    // every thread of a block that pushed fences its own peer stores; thread 0's fence + the barrier inside the
-    // reduction then order them before the ticket
-    if (pushed) __threadfence_system();
-    if (grid_reduce_last_world<CG_NT>(acc, a.partials, a.ticket, red, total, a.comm, __syncthreads_or(pushed), a.comm.world > 1)) {
+    if (grid_reduce_last_world<CG_NT>(acc, a.partials, a.ticket, red, total, a.comm)) {
         if (threadIdx.x == 0) {
             CgScalars* s = a.sc;
             s->r0 = s->r1;
@@ -559,8 +564,6 @@ struct PersistentArgs {
     float* x;                       // z
     float* r;                       // residual (read + written)
     long long n4;
-    int q_per_line;
-    HaloPeers r_halo;
     int passes;                     // max_iter + 1
     unsigned long long* bar;        // grid barrier counter, zero on entry
     double* part[2];                // per-block partials of the two reductions of a pass, gridDim.x doubles each
@@ -605,7 +608,7 @@ __device__ __forceinline__ double grid_allreduce(const PersistentArgs& a, double
     if (a.st.comm.world > 1) {
         // one block talks to the peers; the others pick the world total up from a generation-tagged slot
         if (blockIdx.x == 0) {
-            total = peer_allreduce_scalar<SW_NT>(a.st.comm, total, which == 1);
+            total = peer_allreduce_scalar<SW_NT>(a.st.comm, total, false);
             if (threadIdx.x == 0) {
                 a.world_tot[gen & 3ull] = total;
                 __threadfence();
@@ -646,7 +649,6 @@ __global__ void __launch_bounds__(SW_NT, SRPS_STRIP_MINB) cg_persistent_kernel(c
         const float alpha = (float)r1 / (float)dot;                      // devicecalls.cu:269
         // ---- x += alpha p ; r -= alpha y ; r.r                          devicecalls.cu:270-274
         double acc = 0.0;
-        bool pushed = false;
         const float* pn = st.p_out;
         for (long long i = (long long)blockIdx.x * SW_NT + threadIdx.x; i < a.n4; i += stride) {
             const float4 p4 = ld4(pn + 4 * i), y4 = ld4(st.y + 4 * i);
@@ -655,15 +657,9 @@ __global__ void __launch_bounds__(SW_NT, SRPS_STRIP_MINB) cg_persistent_kernel(c
             r4.x -= alpha * y4.x; r4.y -= alpha * y4.y; r4.z -= alpha * y4.z; r4.w -= alpha * y4.w;
             st4(a.x + 4 * i, x4);
             st4(a.r + 4 * i, r4);
-            if (st.comm.world > 1) {
-                if (a.r_halo.prev_ghost && i < a.q_per_line) { st4(a.r_halo.prev_ghost + 4 * i, r4); pushed = true; }
-                if (a.r_halo.next_ghost && i >= a.n4 - a.q_per_line) { st4(a.r_halo.next_ghost + 4 * (i - (a.n4 - a.q_per_line)), r4); pushed = true; }
-            }
             acc += (double)(r4.x * r4.x + r4.y * r4.y) + (double)(r4.z * r4.z + r4.w * r4.w);
         }
-        if (pushed) __threadfence_system();
-        const bool any_pushed = __syncthreads_or(pushed);
-        const double rr = grid_allreduce(a, acc, 1, gen, red, any_pushed);
+        const double rr = grid_allreduce(a, acc, 1, gen, red, false);
         r0 = r1; r1 = rr; k++;
         beta = (float)r1 / (float)r0;                                    // devicecalls.cu:262
         if (!(((float)r1 > tol2) && (k <= max_iter))) break;             // devicecalls.cu:252

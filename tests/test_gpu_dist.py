@@ -9,8 +9,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("cg", ["persistent", "graph"])
-def test_strip_partition_matches_single_gpu(cg):
+def test_strip_partition_matches_single_gpu():
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -18,7 +17,7 @@ def test_strip_partition_matches_single_gpu(cg):
     world = 2
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "dist_strip_check.py")],
-                         capture_output=True, text=True, timeout=900, env=dict(os.environ, SRPS_CG=cg))
+                         capture_output=True, text=True, timeout=900)
     sys.stdout.write(res.stdout[-4000:])
     sys.stderr.write(res.stderr[-4000:])
     assert res.returncode == 0 and "DIST_OK" in res.stdout
