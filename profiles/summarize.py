@@ -1,0 +1,72 @@
+"""Turns the raw ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/.
+    python profiles/summarize.py r1      (needs ncu on PATH for the --page raw export of the .ncu-rep)"""
+import collections
+import csv
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+src = os.path.join(ROOT, "gpurun_out")
+dst = os.path.join(ROOT, "profiles")
+
+# ---- launch list ---------------------------------------------------------------------------------
+path = os.path.join(src, f"{tag}_launches.csv")
+if os.path.exists(path):
+    lines = [ln for ln in open(path) if not ln.startswith("==")]
+    rd = csv.reader(lines)
+    hdr = next(rd)
+    idx = {h: i for i, h in enumerate(hdr)}
+    agg = collections.OrderedDict()
+    for r in rd:
+        if len(r) < len(hdr) or r[idx["Metric Name"]] != "gpu__time_duration.sum":
+            continue
+        v = float(r[idx["Metric Value"]].replace(",", ""))
+        u = r[idx["Metric Unit"]]
+        v = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)
+        a = agg.setdefault(r[idx["Kernel Name"]], [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    ours = {k: v for k, v in agg.items() if "srps::" in k or "light_consts" in k}
+    tot = sum(v[1] for v in ours.values())
+    out = [f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 700  python bench.py --steps 2 --warmup 1 --no-cpu   (SRPS_NO_GRAPH=1)",
+           "# 4096x4096 HR, sf=4, 32 images; cold-cache serialised launch times: compare SHARES, not absolutes.",
+           "# kernels of this library only (the first 700 launches also contain torch's synthetic-scene generation, omitted); shares within the library",
+           "%-72s %6s %12s %7s %10s" % ("kernel", "count", "total_us", "share", "avg_us")]
+    for k, (n, t) in sorted(ours.items(), key=lambda kv: -kv[1][1]):
+        out.append("%-72s %6d %12.1f %6.1f%% %10.2f" % (k[:72], n, t, 100 * t / tot, t / n))
+    open(os.path.join(dst, f"{tag}_launches_summary.txt"), "w").write("\n".join(out) + "\n")
+    import shutil
+    shutil.copy(path, os.path.join(dst, f"{tag}_launches.csv"))
+    print("\n".join(out))
+
+# ---- full capture ----------------------------------------------------------------------------------
+rep = os.path.join(src, f"{tag}_prof.ncu-rep")
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
+            "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+    out = [f"# ncu --set full --clock-control none --import-source on, bench.py --steps 1 --warmup 1 --no-cpu (4096x4096, sf=4, 32 images), {tag}",
+           "# first captured launch of each kernel", ""]
+    seen = set()
+    for r in rows[2:]:
+        k = r[idx["Kernel Name"]]
+        if k in seen:
+            continue
+        seen.add(k)
+        out.append("## " + k)
+        for w in want:
+            if w in idx:
+                out.append("    %-78s %s %s" % (w, r[idx[w]], units[idx[w]]))
+        out.append("")
+    open(os.path.join(dst, f"{tag}_ncu_full_summary.txt"), "w").write("\n".join(out))
+    print("wrote", f"{tag}_ncu_full_summary.txt", len(seen), "kernels")
