@@ -518,20 +518,33 @@ struct UpdateArgs {
     PeerComm comm;
 };
 
+#ifndef SRPS_UPD_UNROLL
+#define SRPS_UPD_UNROLL 1
+#endif
 __global__ void __launch_bounds__(CG_NT, 4) cg_update_kernel(const UpdateArgs a) {
     __shared__ double red[CG_NT / 32];
     if (!a.sc->active) return;
     const float alpha = a.sc->alpha;
     double acc = 0.0;
     const long long stride = (long long)gridDim.x * CG_NT;
-    for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < a.n4; i += stride) {
-        const float4 p4 = ld4(a.p + 4 * i), y4 = ld4(a.y + 4 * i);
-        float4 x4 = ld4(a.x + 4 * i), r4 = ld4(a.r + 4 * i);
-        x4.x += alpha * p4.x; x4.y += alpha * p4.y; x4.z += alpha * p4.z; x4.w += alpha * p4.w;
-        r4.x -= alpha * y4.x; r4.y -= alpha * y4.y; r4.z -= alpha * y4.z; r4.w -= alpha * y4.w;
-        st4(a.x + 4 * i, x4);
-        st4(a.r + 4 * i, r4);
-        acc += (double)(r4.x * r4.x + r4.y * r4.y) + (double)(r4.z * r4.z + r4.w * r4.w);
+    for (long long i0 = (long long)blockIdx.x * CG_NT + threadIdx.x; i0 < a.n4; i0 += stride * SRPS_UPD_UNROLL) {
+        float4 p4[SRPS_UPD_UNROLL], y4[SRPS_UPD_UNROLL], x4[SRPS_UPD_UNROLL], r4[SRPS_UPD_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SRPS_UPD_UNROLL; u++) {
+            const long long i = i0 + u * stride;
+            if (i < a.n4) { p4[u] = ld4(a.p + 4 * i); y4[u] = ld4(a.y + 4 * i); x4[u] = ld4(a.x + 4 * i); r4[u] = ld4(a.r + 4 * i); }
+        }
+#pragma unroll
+        for (int u = 0; u < SRPS_UPD_UNROLL; u++) {
+            const long long i = i0 + u * stride;
+            if (i < a.n4) {
+                x4[u].x += alpha * p4[u].x; x4[u].y += alpha * p4[u].y; x4[u].z += alpha * p4[u].z; x4[u].w += alpha * p4[u].w;
+                r4[u].x -= alpha * y4[u].x; r4[u].y -= alpha * y4[u].y; r4[u].z -= alpha * y4[u].z; r4[u].w -= alpha * y4[u].w;
+                st4(a.x + 4 * i, x4[u]);
+                st4(a.r + 4 * i, r4[u]);
+                acc += (double)(r4[u].x * r4[u].x + r4[u].y * r4[u].y) + (double)(r4[u].z * r4[u].z + r4[u].w * r4[u].w);
+            }
+        }
     }
     double total;
     if (grid_reduce_last_world<CG_NT>(acc, a.partials, a.ticket, red, total, a.comm)) {

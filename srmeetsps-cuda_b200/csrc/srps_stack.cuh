@@ -16,7 +16,10 @@
 namespace srps {
 
 constexpr int ST_NT = 128;     // threads per CTA in the stack passes
-constexpr int LIGHT_IB = 8;    // images per CTA row in the lighting reduction
+#ifndef SRPS_LIGHT_IB
+#define SRPS_LIGHT_IB 4          // measured at 4096^2 x 32 (round 1): IB=4 / 3 CTAs per SM (168 registers, no spills) 1.21 ms;
+#endif                           // IB=8 / 2 CTAs (255 registers, spills) 1.50 ms; IB=4 / 4 CTAs (128 registers) 1.55 ms
+constexpr int LIGHT_IB = SRPS_LIGHT_IB;    // images per CTA row in the lighting reduction
 constexpr int MAX_IMAGES = 64; // n_images limit (shared-memory copy of s)
 
 // ---------------------------------------------------------------------------------------------
@@ -170,7 +173,10 @@ __device__ inline void light_consts_from_s(const float* s, int n, LightConsts* l
     }
 }
 
-__global__ void __launch_bounds__(ST_NT, 2) lighting_reduce_kernel(const LightArgs a) {
+#ifndef SRPS_LIGHT_MINB
+#define SRPS_LIGHT_MINB 3
+#endif
+__global__ void __launch_bounds__(ST_NT, SRPS_LIGHT_MINB) lighting_reduce_kernel(const LightArgs a) {
     __shared__ double tot[LIGHT_IB * 12];
     __shared__ float wsm[(ST_NT / 32) * LIGHT_IB * 12];
     const int group = blockIdx.y;
@@ -283,8 +289,15 @@ struct ProjectArgs {
     long long n4;
 };
 
+#ifndef SRPS_PROJ_MINB
+#define SRPS_PROJ_MINB 3
+#endif
+#ifndef SRPS_PROJ_UNROLL
+#define SRPS_PROJ_UNROLL 4       // images in flight per thread; measured at 4096^2 x 32 (round 1): 4 -> 1.18 ms, 2 -> 1.38 ms
+#endif
+constexpr int PROJ_UNROLL = SRPS_PROJ_UNROLL;
 template <bool FUSED>
-__global__ void __launch_bounds__(ST_NT, 3) stack_project_kernel(const ProjectArgs a) {
+__global__ void __launch_bounds__(ST_NT, SRPS_PROJ_MINB) stack_project_kernel(const ProjectArgs a) {
     __shared__ float4 s_sm[MAX_IMAGES * 3];
     for (int e = threadIdx.x; e < a.n_images * 3; e += ST_NT) s_sm[e] = *reinterpret_cast<const float4*>(a.s + 4 * e);
     __syncthreads();
@@ -301,7 +314,7 @@ __global__ void __launch_bounds__(ST_NT, 3) stack_project_kernel(const ProjectAr
             for (int k = 0; k < 4; k++) U[c][k] = f4zero();
         }
         const float* base = a.I + 4 * i;
-#pragma unroll 2
+#pragma unroll PROJ_UNROLL
         for (int j = 0; j < a.n_images; j++) {
             float4 v[3];
 #pragma unroll
