@@ -370,15 +370,15 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
         const int jB = min(jA + a.strip_cl, ny);
         const float yy0 = (float)(g.ib0 + x) - g.cy;
 
-        // Loads are UNCONDITIONAL with a clamped address (the plane origin is always valid) and a select on the result:
-        // no branch regions, so the ~24 loads of a group are issued back to back.  Read-only operands use the
-        // non-coherent path (nothing read here is written here: the new p goes to the other ping-pong plane).
-        // Strip partition: r on a ghost line (j = -1 / ny) is read in place from the neighbour's boundary line over
-        // NVLink (pointer select).  Peer lines may sit in this SM's L1 only within one launch; every pass is its own
-        // launch (the single-launch persistent CG is not used with a strip partition).
-        auto zsel = [](float4 v, bool ok) -> float4 {
-            return make_float4(ok ? v.x : 0.f, ok ? v.y : 0.f, ok ? v.z : 0.f, ok ? v.w : 0.f);
-        };
+        // Loads are UNCONDITIONAL with a clamped address (the plane origin is always valid): no branch regions, so the
+        // ~24 loads of a group are issued back to back.  What a clamped load returns is never zeroed: it can only belong to
+        // (a) a lane beyond the line pitch -- a non-writing halo lane whose only consumer is the pad pixel of the last
+        // valid float4 (type 0, forced to 0), or (b) a line beyond the guard/ghost line ny -- never an output line, never
+        // the lower neighbour of one, and outside every sf x sf block of an output line (ny is a multiple of sf).
+        // Read-only operands use the non-coherent path (nothing read here is written here: the new p goes to the other
+        // ping-pong plane).  Strip partition: r on a ghost line (j = -1 / ny) is read in place from the neighbour's
+        // boundary line over NVLink (pointer select).  Peer lines may sit in this SM's L1 only within one launch; every
+        // pass is its own launch (the single-launch persistent CG is not used with a strip partition).
         auto load_pn = [&](int j) -> float4 {
             const bool ok = colok && j <= ny;                      // line ny is the zero guard (or ghost) line
             const long long off = ok ? (long long)j * pitch + x : 0;
@@ -387,19 +387,18 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
                 rs = (ok && j < 0 && a.r_prev_line) ? a.r_prev_line + x : rs;
                 rs = (ok && j == ny && a.r_next_line) ? a.r_next_line + x : rs;
                 const float4 r4 = ldg4(rs), p4 = ldg4(a.p_in + off);
-                return zsel(make_float4(r4.x + beta * p4.x, r4.y + beta * p4.y, r4.z + beta * p4.z, r4.w + beta * p4.w), ok);
+                return make_float4(r4.x + beta * p4.x, r4.y + beta * p4.y, r4.z + beta * p4.z, r4.w + beta * p4.w);
             }
-            return zsel(ldg4(a.vin + off), ok);
+            return ldg4(a.vin + off);
         };
         auto load_t = [&](int j) -> unsigned {
             const bool ok = colok && j <= ny;
-            const unsigned t = __ldg(reinterpret_cast<const unsigned*>(a.types + (ok ? (long long)j * pitch + x : 0)));
-            return ok ? t : 0u;
+            return __ldg(reinterpret_cast<const unsigned*>(a.types + (ok ? (long long)j * pitch + x : 0)));
         };
         auto load_w = [&](int j, float4& w0, float4& w1, float4& w2) {
             const bool ok = colok && j <= ny;
             const long long off = ok ? (long long)j * pitch + x : 0;
-            w0 = zsel(ldg4(a.w0 + off), ok); w1 = zsel(ldg4(a.w1 + off), ok); w2 = zsel(ldg4(a.w2 + off), ok);
+            w0 = ldg4(a.w0 + off); w1 = ldg4(a.w1 + off); w2 = ldg4(a.w2 + off);
         };
 
         float4 pl[SW_G + 1], wl0[SW_G + 1], wl1[SW_G + 1], wl2[SW_G + 1];
