@@ -45,6 +45,7 @@ struct srps_ctx {
     int* idx = nullptr; int* idx_lr = nullptr;
     float* I = nullptr; float* I_base = nullptr;
     float *z = nullptr, *r = nullptr, *p = nullptr, *p2 = nullptr, *y = nullptr, *e0 = nullptr, *dz = nullptr, *dz_new = nullptr;
+    float *r2 = nullptr, *y2 = nullptr;     // second residual / A p planes of the fused CG pass (ping-pong)
     float *w[3]{}, *gq[3]{}, *N[3]{}, *N_new[3]{}, *rho[3]{};
     float *U = nullptr, *ad[3]{}, *ar[3]{}, *ap[3]{};    // reference-CG albedo only
     float* z0lr = nullptr;
@@ -61,6 +62,7 @@ struct srps_ctx {
     int tiles_x = 0, tiles_y = 0;
     int use_strip = 0, strip_n = 0, strip_chunks = 0, strip_cl = 0, grid_strip = 0;
     int use_persistent = 0, grid_persistent = 0;      // all CG passes in one cooperative launch
+    int use_fused = 0;                                // one kernel per CG pass (cg_fused_kernel)
     unsigned long long* sync_words = nullptr;         // [0] grid barrier counter, [1] world generation, [2..5] world totals (as double)
     long long n4 = 0;
     cudaGraphExec_t cg_graph = nullptr;
@@ -249,7 +251,7 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         ctx->z = next(); ctx->r = next(); ctx->p = next(); ctx->y = next(); ctx->e0 = next(); ctx->dz = next(); ctx->dz_new = next();
         for (int c = 0; c < 3; c++) { ctx->w[c] = next(); ctx->gq[c] = next(); ctx->N[c] = next(); ctx->N_new[c] = next(); ctx->rho[c] = next(); }
         ctx->p2 = next();
-        k += 2;   // spare
+        ctx->r2 = next(); ctx->y2 = next();
         if (refcg) for (int c = 0; c < 3; c++) { ctx->ad[c] = next(); ctx->ar[c] = next(); ctx->ap[c] = next(); }
     }
     if (refcg) {
@@ -326,6 +328,8 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         // Default: persistent below 3 M pixels on one GPU; SRPS_CG=persistent|graph overrides.
         const bool want = ctx->world == 1 && (cgm ? strcmp(cgm, "persistent") == 0 : npix < 3000000);
         ctx->use_persistent = ctx->use_strip && coop && occ_p > 0 && want;
+        // one fused kernel per pass instead of operator + update (SRPS_CG=fused); needs the warp-strip operator
+        ctx->use_fused = ctx->use_strip && !ctx->use_persistent && cgm && strcmp(cgm, "fused") == 0;
         ctx->grid_persistent = std::min(ctx->grid_strip, ctx->sm_count * std::max(1, occ_p));
         CK(cudaMalloc(&ctx->sync_words, 8 * sizeof(unsigned long long)));
         CK(cudaMemsetAsync(ctx->sync_words, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -343,7 +347,7 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, normals_energy_kernel<true>, EP_NT, 0));
     ctx->grid_ep = (int)std::min<long long>((ctx->n4 + EP_NT - 1) / EP_NT, (long long)ctx->sm_count * std::max(1, occ));
     ctx->grid_al = (int)std::min<long long>((ctx->n4 + AL_NT - 1) / AL_NT, (long long)ctx->sm_count * 4);
-    long long pl = std::max<long long>({(long long)ctx->grid_stencil, (long long)ctx->grid_strip, (long long)ctx->grid_update, (long long)ctx->grid_ep,
+    long long pl = std::max<long long>({(long long)ctx->grid_stencil, 4ll * ctx->grid_strip, (long long)ctx->grid_update, (long long)ctx->grid_ep,
                                         3ll * ctx->grid_al, 30ll * ctx->grid_gram,
                                         (long long)LIGHT_IB * 12 * ctx->grid_light_x * ctx->light_groups}) + 64;
     ctx->partials_len = pl;
@@ -637,6 +641,22 @@ extern "C" int srps_albedo(srps_ctx* ctx) {
     return 0;
 }
 
+// The neighbours' boundary lines of plane `local_plane` (their last / first owned line), read in place over NVLink.
+static void peer_boundary_lines(const srps_ctx* ctx, const float* local_plane, const float*& prev_line, const float*& next_line) {
+    prev_line = nullptr; next_line = nullptr;
+    if (!ctx->connected) return;
+    const Grid& g = ctx->g;
+    const long long k = (local_plane - g.origin() - ctx->plane_base) / g.plane;      // plane index: same order on every rank
+    if (ctx->rank > 0) {
+        const int q = ctx->rank - 1;
+        prev_line = (const float*)ctx->peer_planes[q] + k * ctx->peer_plane[q] + g.origin() + (long long)(ctx->peer_ny[q] - 1) * g.pitch;
+    }
+    if (ctx->rank + 1 < ctx->world) {
+        const int q = ctx->rank + 1;
+        next_line = (const float*)ctx->peer_planes[q] + k * ctx->peer_plane[q] + g.origin();
+    }
+}
+
 static void fill_stencil_args(srps_ctx* ctx, StencilArgs& sa) {
     sa.g = ctx->g; sa.types = ctx->types; sa.w0 = ctx->w[0]; sa.w1 = ctx->w[1]; sa.w2 = ctx->w[2]; sa.lc = ctx->lc;
     sa.vin = ctx->z; sa.r = ctx->r; sa.p_in = ctx->p; sa.p_out = ctx->p2; sa.y = ctx->y; sa.g0 = ctx->gq[0]; sa.g1 = ctx->gq[1]; sa.g2 = ctx->gq[2];
@@ -644,19 +664,8 @@ static void fill_stencil_args(srps_ctx* ctx, StencilArgs& sa) {
     sa.tiles_x = ctx->tiles_x; sa.tiles_y = ctx->tiles_y;
     sa.strip_n = ctx->strip_n; sa.strip_chunks = ctx->strip_chunks; sa.strip_cl = ctx->strip_cl;
     sa.comm = ctx->comm;
-    sa.r_prev_line = nullptr; sa.r_next_line = nullptr;
-    if (ctx->connected) {       // the neighbours' boundary lines of r, read in place over NVLink
-        const Grid& g = ctx->g;
-        const long long k = (ctx->r - g.origin() - ctx->plane_base) / g.plane;
-        if (ctx->rank > 0) {
-            const int q = ctx->rank - 1;
-            sa.r_prev_line = (const float*)ctx->peer_planes[q] + k * ctx->peer_plane[q] + g.origin() + (long long)(ctx->peer_ny[q] - 1) * g.pitch;
-        }
-        if (ctx->rank + 1 < ctx->world) {
-            const int q = ctx->rank + 1;
-            sa.r_next_line = (const float*)ctx->peer_planes[q] + k * ctx->peer_plane[q] + g.origin();
-        }
-    }
+    peer_boundary_lines(ctx, ctx->r, sa.r_prev_line, sa.r_next_line);
+    sa.y_in = nullptr; sa.r_out = nullptr; sa.x = nullptr; sa.y_prev_line = nullptr; sa.y_next_line = nullptr; sa.plane = 0;
 }
 
 // Ghost-line addresses of plane `local_plane` inside the two neighbours' (mapped) plane allocations.
@@ -716,6 +725,48 @@ static int launch_cg_iterations(srps_ctx* ctx, StencilArgs sa, UpdateArgs ua, in
     return 0;
 }
 
+// Fused form: pass k reads r[k&1], y[k&1], p[k&1] and writes the other planes; pass 0 has no pending step.
+static void set_fused_pass(srps_ctx* ctx, StencilArgs& sa, int k) {
+    float* rr[2] = {ctx->r, ctx->r2};
+    float* yy[2] = {ctx->y, ctx->y2};
+    float* pp[2] = {ctx->p, ctx->p2};
+    sa.r = rr[k & 1]; sa.r_out = rr[(k + 1) & 1];
+    sa.y_in = yy[k & 1]; sa.y = yy[(k + 1) & 1];
+    sa.p_in = pp[k & 1]; sa.p_out = pp[(k + 1) & 1];
+    sa.plane = (k + 1) & 1;
+    sa.x = ctx->z;
+    peer_boundary_lines(ctx, sa.r, sa.r_prev_line, sa.r_next_line);
+    peer_boundary_lines(ctx, sa.y_in, sa.y_prev_line, sa.y_next_line);
+}
+
+static void launch_fused_pass(srps_ctx* ctx, const StencilArgs& sa, bool first) {
+    const int sf = ctx->g.sf;
+    if (first) {
+        if (sf == 1) LAUNCH(ctx, (cg_fused_kernel<1, true>), ctx->grid_strip, SW_NT, sa);
+        else if (sf == 2) LAUNCH(ctx, (cg_fused_kernel<2, true>), ctx->grid_strip, SW_NT, sa);
+        else LAUNCH(ctx, (cg_fused_kernel<4, true>), ctx->grid_strip, SW_NT, sa);
+    } else {
+        if (sf == 1) LAUNCH(ctx, (cg_fused_kernel<1, false>), ctx->grid_strip, SW_NT, sa);
+        else if (sf == 2) LAUNCH(ctx, (cg_fused_kernel<2, false>), ctx->grid_strip, SW_NT, sa);
+        else LAUNCH(ctx, (cg_fused_kernel<4, false>), ctx->grid_strip, SW_NT, sa);
+    }
+}
+
+static void launch_fused_tail(srps_ctx* ctx) {
+    TailArgs ta{};
+    ta.x = ctx->z; ta.p[0] = ctx->p; ta.p[1] = ctx->p2; ta.n4 = ctx->n4; ta.sc = ctx->sc;
+    LAUNCH(ctx, cg_tail_kernel, ctx->grid_update, CG_NT, ta);
+}
+
+static int launch_cg_fused(srps_ctx* ctx, StencilArgs sa, int passes) {
+    for (int k = 0; k < passes; k++) {
+        set_fused_pass(ctx, sa, k);
+        launch_fused_pass(ctx, sa, k == 0);
+    }
+    launch_fused_tail(ctx);
+    return 0;
+}
+
 extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
     if (!ctx) return SRPS_E_INVALID;
     if (!ctx->have_state) return fail(ctx, SRPS_E_STATE, "no state uploaded");
@@ -764,30 +815,36 @@ extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
         // debugging aid: one pass at a time, CG scalars printed after each (no graph)
         for (int k = 0; k < passes; k++) {
             StencilArgs s1 = sa; UpdateArgs u1 = ua;
-            s1.p_in = (k & 1) ? ctx->p2 : ctx->p; s1.p_out = (k & 1) ? ctx->p : ctx->p2; u1.p = s1.p_out;
-            launch_operator<MODE_ITER>(ctx, s1);
-            LAUNCH(ctx, cg_update_kernel, ctx->grid_update, CG_NT, u1);
+            if (ctx->use_fused) {
+                set_fused_pass(ctx, s1, k);
+                launch_fused_pass(ctx, s1, k == 0);
+            } else {
+                s1.p_in = (k & 1) ? ctx->p2 : ctx->p; s1.p_out = (k & 1) ? ctx->p : ctx->p2; u1.p = s1.p_out;
+                launch_operator<MODE_ITER>(ctx, s1);
+                LAUNCH(ctx, cg_update_kernel, ctx->grid_update, CG_NT, u1);
+            }
             CK(cudaMemcpyAsync(ctx->h_sc, ctx->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             fprintf(stderr, "[srps rank %d] pass %3d: r1 %.6e r0 %.6e p.Ap %.6e alpha %.6e beta %.6e k %d active %d\n", ctx->rank, k,
                     ctx->h_sc[0].r1, ctx->h_sc[0].r0, ctx->h_sc[0].dot, ctx->h_sc[0].alpha, ctx->h_sc[0].beta, ctx->h_sc[0].k, ctx->h_sc[0].active);
             if (!ctx->h_sc[0].active) break;
         }
+        if (ctx->use_fused) launch_fused_tail(ctx);
     } else if (ctx->use_graph) {
         if (!ctx->cg_graph) {
             cudaGraph_t graph = nullptr;
             const long long before = ctx->launches;
             CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-            launch_cg_iterations(ctx, sa, ua, passes);
+            if (ctx->use_fused) launch_cg_fused(ctx, sa, passes); else launch_cg_iterations(ctx, sa, ua, passes);
             CK(cudaStreamEndCapture(ctx->stream, &graph));
             ctx->launches = before;
             CK(cudaGraphInstantiate(&ctx->cg_graph, graph, 0));
             CK(cudaGraphDestroy(graph));
         }
         CK(cudaGraphLaunch(ctx->cg_graph, ctx->stream));
-        ctx->launches += 2ll * passes;
+        ctx->launches += ctx->use_fused ? passes + 1ll : 2ll * passes;
     } else {
-        launch_cg_iterations(ctx, sa, ua, passes);
+        if (ctx->use_fused) launch_cg_fused(ctx, sa, passes); else launch_cg_iterations(ctx, sa, ua, passes);
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));

@@ -21,7 +21,7 @@ constexpr int RL = TY + 2;         // region lines (tile + one halo line each si
 constexpr int SP = TX + 16;        // smem pitch of P/T: region col rc (0..TX+7) stored at rc+4
 constexpr int Q1P = TX + 8;        // smem pitch of Q1: interior col ic (-1..TX) stored at ic+4
 
-enum { MODE_ITER = 0, MODE_INIT = 1, MODE_APPLY = 2 };
+enum { MODE_ITER = 0, MODE_INIT = 1, MODE_APPLY = 2, MODE_FUSED = 3, MODE_FUSED0 = 4 };
 
 struct StencilArgs {
     Grid g;
@@ -50,6 +50,14 @@ struct StencilArgs {
     // neighbour finished writing r before this pass starts, so no halo push and no system-scope fence is needed.
     const float* r_prev_line;              // previous rank's line ny_prev-1 of r
     const float* r_next_line;              // next rank's line 0 of r
+    // MODE_FUSED / MODE_FUSED0 (one kernel per CG pass, see cg_fused_kernel): the pending update of the previous pass
+    //   r <- r - alpha y_in (written to r_out), z += alpha p_in, then p_out <- r + beta p_in, y <- A p_out
+    const float* y_in;                     // previous pass's A p (read, window + halo; ghost lines pulled like r)
+    float* r_out;                          // the other residual plane
+    float* x;                              // z
+    const float* y_prev_line;              // previous rank's line ny_prev-1 of y_in
+    const float* y_next_line;              // next rank's line 0 of y_in
+    int plane;                             // which ping-pong plane p_out is (recorded for cg_tail_kernel)
 };
 
 struct StencilSmem {
@@ -350,8 +358,12 @@ __device__ __forceinline__ LineQ line_q(const LightConsts& lc, float fx, float f
 // One application of the operator over this block's share of the (strip, chunk) items.  `a.p_in` / `a.p_out`
 // are the ping-pong planes of this pass; returns this thread's partial of p.y (MODE_ITER).
 template <int MODE, int SF>
-__device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightConsts& lc, float beta) {
-    static_assert(MODE == MODE_ITER || MODE == MODE_APPLY, "the warp-strip kernel implements ITER and APPLY");
+__device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightConsts& lc, float beta, float alpha = 0.f,
+                                             double* extra = nullptr /* FUSED: r.r, r.y, y.y */) {
+    static_assert(MODE == MODE_ITER || MODE == MODE_APPLY || MODE == MODE_FUSED || MODE == MODE_FUSED0,
+                  "the warp-strip kernel implements ITER, APPLY and the fused pass");
+    constexpr bool FUSED = (MODE == MODE_FUSED || MODE == MODE_FUSED0);
+    constexpr bool KEEPS_P = (MODE == MODE_ITER) || FUSED;      // writes the new search direction
     static_assert(SF == 1 || SF == 2 || SF == 4, "sf must divide the group height");
     const Grid& g = a.g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -359,7 +371,7 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
     const float inv4 = 1.f / (float)(SF * SF * SF * SF);
     const unsigned FULL = 0xffffffffu;
     const int nitems = a.strip_n * a.strip_chunks;
-    double dot = 0.0;
+    double dot = 0.0, s_rr = 0.0, s_ry = 0.0, s_yy = 0.0;
 
     for (int item = blockIdx.x * (SW_NT / 32) + warp; item < nitems; item += gridDim.x * (SW_NT / 32)) {
         const int strip = item % a.strip_n, chunk = item / a.strip_n;
@@ -391,6 +403,39 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
             }
             return ldg4(a.vin + off);
         };
+        // fused pass: the previous pass's residual update is applied on the fly (window AND halo: the halo is recomputed
+        // redundantly, like p), rn = r - alpha y_in ; returns p = rn + beta p_in ; pin = p_in (for the z update)
+        auto load_fused = [&](int j, float4& rn, float4& pin) -> float4 {
+            const bool ok = colok && j <= ny;
+            const long long off = ok ? (long long)j * pitch + x : 0;
+            const float* rs = a.r + off;
+            rs = (ok && j < 0 && a.r_prev_line) ? a.r_prev_line + x : rs;
+            rs = (ok && j == ny && a.r_next_line) ? a.r_next_line + x : rs;
+            const float4 r4 = ldg4(rs);
+            if (MODE == MODE_FUSED0) { rn = r4; pin = f4zero(); return r4; }       // first pass: p = r
+            const float* ys = a.y_in + off;
+            ys = (ok && j < 0 && a.y_prev_line) ? a.y_prev_line + x : ys;
+            ys = (ok && j == ny && a.y_next_line) ? a.y_next_line + x : ys;
+            const float4 y4 = ldg4(ys);
+            pin = ldg4(a.p_in + off);
+            rn = make_float4(r4.x - alpha * y4.x, r4.y - alpha * y4.y, r4.z - alpha * y4.z, r4.w - alpha * y4.w);
+            return make_float4(rn.x + beta * pin.x, rn.y + beta * pin.y, rn.z + beta * pin.z, rn.w + beta * pin.w);
+        };
+        // z is read and written by this kernel (each float4 by its owner only): coherent load, clamped like the others
+        auto load_x = [&](int j) -> float4 {
+            const bool ok = colok && j <= ny;
+            return ld4(a.x + (ok ? (long long)j * pitch + x : 0));
+        };
+        // owner's stores of a freshly loaded line: the new residual, the pending z step, and r.r
+        auto store_owned = [&](int j, const float4& rn, const float4& xo, const float4& pin) {
+            if (writer && j < jB) {
+                const long long off = (long long)j * pitch + x;
+                st4(a.r_out + off, rn);
+                if (MODE == MODE_FUSED)
+                    st4(a.x + off, make_float4(xo.x + alpha * pin.x, xo.y + alpha * pin.y, xo.z + alpha * pin.z, xo.w + alpha * pin.w));
+                s_rr += (double)((rn.x * rn.x + rn.y * rn.y) + (rn.z * rn.z + rn.w * rn.w));
+            }
+        };
         auto load_t = [&](int j) -> unsigned {
             const bool ok = colok && j <= ny;
             return __ldg(reinterpret_cast<const unsigned*>(a.types + (ok ? (long long)j * pitch + x : 0)));
@@ -402,28 +447,43 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
         };
 
         float4 pl[SW_G + 1], wl0[SW_G + 1], wl1[SW_G + 1], wl2[SW_G + 1];
+        float4 rl[SW_G + 1];                    // FUSED: residual window (r.y is formed when y leaves the pipeline)
         unsigned tl[SW_G + 1];
         float4 pprev, q0f_prev;
         {   // prologue: the forward x-rows of line jA-1 reach line jA
             float4 w0, w1, w2;
-            pprev = load_pn(jA - 1);
+            float4 pin0 = f4zero(), x0 = f4zero();
+            if (FUSED) { float4 rdum, pdum; pprev = load_fused(jA - 1, rdum, pdum); } else pprev = load_pn(jA - 1);
             const unsigned tp = load_t(jA - 1);
             load_w(jA - 1, w0, w1, w2);
-            pl[0] = load_pn(jA); tl[0] = load_t(jA); load_w(jA, wl0[0], wl1[0], wl2[0]);
+            if (FUSED) { pl[0] = load_fused(jA, rl[0], pin0); if (MODE == MODE_FUSED) x0 = load_x(jA); } else pl[0] = load_pn(jA);
+            tl[0] = load_t(jA); load_w(jA, wl0[0], wl1[0], wl2[0]);
+            if (FUSED) store_owned(jA, rl[0], x0, pin0);
             const float left = __shfl_up_sync(FULL, pprev.w, 1), right = __shfl_down_sync(FULL, pprev.x, 1);
             const float xx = (float)(g.jb0 + jA - 1) - g.cx;
             const LineQ q = line_q(lc, g.fx, g.fy, xx, yy0, tp & 0xfbfbfbfbu /* backward x-rows not needed */, pprev, f4zero(),
                                    pl[0], left, right, w0, w1, w2);
             q0f_prev = q.q0f;
             // strip partition: keep the search direction on the ghost line above current (recomputed redundantly)
-            if (MODE == MODE_ITER && a.comm.world > 1 && chunk == 0 && writer) st4(a.p_out - pitch + x, pprev);
+            if (KEEPS_P && a.comm.world > 1 && chunk == 0 && writer) st4(a.p_out - pitch + x, pprev);
         }
         for (int j0 = jA; j0 < jB; j0 += SW_G) {
+            float4 pin[SW_G + 1], xo[SW_G + 1];
 #pragma unroll
             for (int l = 1; l <= SW_G; l++) {
-                pl[l] = load_pn(j0 + l); tl[l] = load_t(j0 + l); load_w(j0 + l, wl0[l], wl1[l], wl2[l]);
+                if (FUSED) {
+                    pl[l] = load_fused(j0 + l, rl[l], pin[l]);
+                    xo[l] = (MODE == MODE_FUSED) ? load_x(j0 + l) : f4zero();
+                } else {
+                    pl[l] = load_pn(j0 + l);
+                }
+                tl[l] = load_t(j0 + l); load_w(j0 + l, wl0[l], wl1[l], wl2[l]);
             }
-            if (MODE == MODE_ITER && a.comm.world > 1 && j0 + SW_G >= ny && writer) {      // ghost line below: keep p there too
+            if (FUSED) {                        // after the whole batch of loads: stores inside it would serialise them
+#pragma unroll
+                for (int l = 1; l <= SW_G; l++) store_owned(j0 + l, rl[l], xo[l], pin[l]);
+            }
+            if (KEEPS_P && a.comm.world > 1 && j0 + SW_G >= ny && writer) {      // ghost line below: keep p there too
 #pragma unroll
                 for (int l = 1; l <= SW_G; l++)
                     if (j0 + l == ny) st4(a.p_out + (long long)ny * pitch + x, pl[l]);
@@ -459,7 +519,7 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
                 const float q1fv[5] = {q1f_left, q.q1f.x, q.q1f.y, q.q1f.z, q.q1f.w};
                 const float q1bv[5] = {q.q1b.x, q.q1b.y, q.q1b.z, q.q1b.w, q1b_right};
                 float4 out;
-                float dl = 0.f;
+                float dl = 0.f, dry = 0.f, dyy = 0.f;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const unsigned t = (tl[l] >> (8 * k)) & 0xffu;
@@ -471,19 +531,22 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
                     if (!(t & T_MASK)) yv = 0.f;
                     f4set(out, k, yv);
                     dl += f4get(pc, k) * yv;
+                    if (FUSED) { dry += f4get(rl[l], k) * yv; dyy += yv * yv; }
                 }
                 if (writer && j < jB) {
                     const long long off = (long long)j * pitch + x;
                     st4(a.y + off, out);
-                    if (MODE == MODE_ITER) { st4(a.p_out + off, pc); dot += (double)dl; }
+                    if (KEEPS_P) { st4(a.p_out + off, pc); dot += (double)dl; }
+                    if (FUSED) { s_ry += (double)dry; s_yy += (double)dyy; }
                 }
                 q0f_prev = q.q0f;
             }
             pprev = pl[SW_G - 1];
             pl[0] = pl[SW_G]; tl[0] = tl[SW_G]; wl0[0] = wl0[SW_G]; wl1[0] = wl1[SW_G]; wl2[0] = wl2[SW_G];
+            if (FUSED) rl[0] = rl[SW_G];
         }
     }
-
+    if (FUSED) { extra[0] = s_rr; extra[1] = s_ry; extra[2] = s_yy; }
     return dot;
 }
 
@@ -555,6 +618,114 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_update_kernel(const UpdateArgs a)
             s->beta = (float)total / (float)s->r0;                                  // devicecalls.cu:262
             s->active = ((float)total > s->tol2) && (s->k <= s->max_iter);          // devicecalls.cu:252
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused CG pass: ONE kernel and ONE reduction per pass (sf <= 4).
+//
+// The two-kernel form needs r.r of the updated residual before it can form beta, hence the separate update kernel
+// and a second grid-wide (and, with a strip partition, cross-GPU) reduction per pass.  Here pass k applies the update
+// of pass k-1 on the fly while it loads its operands,
+//     r_k = r_{k-1} - alpha_{k-1} y_{k-1}        (window + halo, written to the other r plane)
+//     z  += alpha_{k-1} p_{k-1}
+//     p_k = r_k + beta_k p_{k-1} ,  y_k = A p_k
+// and reduces four dots at once: S0 = r_k.r_k, S1 = p_k.y_k, S2 = r_k.y_k, S3 = y_k.y_k.  Then
+//     alpha_k    = S0 / S1                                   devicecalls.cu:269  (r.r measured, as in the reference)
+//     |r_{k+1}|^2 = S0 - 2 alpha_k S2 + alpha_k^2 S3          (= |r_k - alpha_k y_k|^2 expanded, fp64)
+//     beta_{k+1} = |r_{k+1}|^2 / S0                          devicecalls.cu:262
+// so only beta rests on the expanded norm, for one pass; the next pass measures r.r again (no drift).  The stop test
+// r.r > tol^2 (devicecalls.cu:252) uses the MEASURED value one pass late: a pass that finds S0 <= tol^2 is void -- it has
+// already applied the previous step to z, cancels its own, and leaves k where the reference's loop would.
+// Algorithmic traffic: 44 B/pixel/pass (r, y, p, z, 3 w read; r, p, y, z written) against 52 for the two-kernel form.
+// cg_tail_kernel applies the step that is still pending after the last pass.
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ bool grid_reduce_last4(const double (&v)[4], double* partials, unsigned* ticket, double* wsm /* [NT/32][4] */,
+                                                  double* tot /* smem [4] */) {
+    static_assert(NT == 128, "one warp per value in the final sum");
+    __shared__ int s_last4;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const double s = warp_sum(v[i]);
+        if (lane == 0) wsm[wid * 4 + i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double b = 0.0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; w++) b += wsm[w * 4 + threadIdx.x];
+        partials[(long long)blockIdx.x * 4 + threadIdx.x] = b;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        s_last4 = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last4) return false;
+    __threadfence();
+    double acc = 0.0;                       // warp `wid` sums value `wid` over the blocks: fixed order
+    for (int b = lane; b < (int)gridDim.x; b += 32) acc += __ldcg(partials + (long long)b * 4 + wid);
+    acc = warp_sum(acc);
+    if (lane == 0) tot[wid] = acc;
+    if (threadIdx.x == 0) *ticket = 0u;
+    __syncthreads();
+    return true;
+}
+
+#ifndef SRPS_FUSED_MINB
+#define SRPS_FUSED_MINB 3
+#endif
+template <int SF, bool FIRST>
+__global__ void __launch_bounds__(SW_NT, SRPS_FUSED_MINB) cg_fused_kernel(const StencilArgs a) {
+    __shared__ double wsm[(SW_NT / 32) * 4];
+    __shared__ double tot[4];
+    if (!a.sc->active) return;
+    const float beta = FIRST ? 0.f : a.sc->beta;
+    const float alpha = FIRST ? 0.f : a.sc->alpha;          // the step of the previous pass, still pending
+    const LightConsts lc = *a.lc;
+    double ex[3];
+    const double py = strip_pass<FIRST ? MODE_FUSED0 : MODE_FUSED, SF>(a, lc, beta, alpha, ex);
+    const double v[4] = {ex[0], py, ex[1], ex[2]};
+    if (!grid_reduce_last4<SW_NT>(v, a.partials, a.ticket, wsm, tot)) return;
+    peer_allreduce_small<SW_NT, 4>(a.comm, tot, false);
+    if (threadIdx.x == 0) {
+        CgScalars* s = a.sc;
+        const double S0 = tot[0], S1 = tot[1], S2 = tot[2], S3 = tot[3];
+        if (!((float)S0 > s->tol2)) {            // the reference left its loop before this pass (devicecalls.cu:252)
+            s->r1 = S0;
+            s->alpha = 0.f;                      // nothing pending: the previous step went into z above
+            s->active = 0;
+        } else {
+            const float al = (float)S0 / (float)S1;                                // devicecalls.cu:269
+            const double rr = S0 - 2.0 * (double)al * S2 + (double)al * (double)al * S3;
+            s->dot = S1;
+            s->alpha = al;
+            s->r0 = S0;
+            s->r1 = rr;
+            s->beta = (float)rr / (float)S0;                                       // devicecalls.cu:262
+            s->k += 1;
+            s->plane = a.plane;
+            s->active = (s->k <= s->max_iter);                                     // devicecalls.cu:252 (k part)
+        }
+    }
+}
+
+// z += alpha p of the last valid pass (alpha == 0: the last pass was void or no pass ran)
+struct TailArgs { float* x; const float* p[2]; long long n4; const CgScalars* sc; };
+__global__ void __launch_bounds__(CG_NT, 4) cg_tail_kernel(const TailArgs a) {
+    const float alpha = a.sc->alpha;
+    if (alpha == 0.f) return;
+    const float* p = (a.sc->plane & 1) ? a.p[1] : a.p[0];
+    const long long stride = (long long)gridDim.x * CG_NT;
+    for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < a.n4; i += stride) {
+        const float4 p4 = ld4(p + 4 * i);
+        float4 x4 = ld4(a.x + 4 * i);
+        x4.x += alpha * p4.x; x4.y += alpha * p4.y; x4.z += alpha * p4.z; x4.w += alpha * p4.w;
+        st4(a.x + 4 * i, x4);
     }
 }
 

@@ -21,10 +21,11 @@ namespace srps {
 constexpr int MAX_RANKS = 8;
 constexpr int MB_SLOTS = 4;
 constexpr int MB_VALS = 800;      // doubles per (slot, source rank): lighting needs n*12 <= 768
+constexpr int MB_SMALL = 4;       // doubles per (slot, source rank) on the latency-optimised path (fused CG pass: 4 dots)
 
 struct Mailbox {
     unsigned long long flag[MB_SLOTS][MAX_RANKS];
-    unsigned long long ll[MB_SLOTS][MAX_RANKS][2];     // scalar fast path: {seq32 | low word}, {seq32 | high word}
+    unsigned long long ll[MB_SLOTS][MAX_RANKS][2 * MB_SMALL];   // fast path: per fp64 value {seq32 | low word}, {seq32 | high word}
     double val[MB_SLOTS][MAX_RANKS][MB_VALS];
 };
 
@@ -130,6 +131,45 @@ __device__ __forceinline__ double peer_allreduce_scalar(const PeerComm& c, doubl
     for (int r = 0; r < c.world; r++) total += s_part[r];      // rank order: identical bits on every rank
     if (threadIdx.x == 0) *c.seq = seq;
     return total;
+}
+
+// The same for NV <= MB_SMALL values at once (the four dot products of a fused CG pass): thread (r, w) sends word w to
+// rank r and waits for rank r's word w.  vals: shared memory of the calling block, world totals on return.
+template <int NT, int NV>
+__device__ __forceinline__ void peer_allreduce_small(const PeerComm& c, double* vals, bool release) {
+    static_assert(NV <= MB_SMALL && MAX_RANKS * 2 * NV <= NT, "one thread per (rank, word)");
+    if (c.world <= 1) return;
+    __shared__ double s_part[MAX_RANKS][NV];
+    __shared__ unsigned s_lo[MAX_RANKS][NV];
+    __shared__ unsigned long long s_seqn;
+    if (threadIdx.x == 0) s_seqn = *c.seq + 1ull;
+    __syncthreads();
+    const unsigned long long seq = s_seqn;
+    const unsigned long long tag = (seq & 0xffffffffull) << 32;
+    const int slot = (int)(seq & (MB_SLOTS - 1));
+    const int t = threadIdx.x / (2 * NV), w = threadIdx.x % (2 * NV);
+    const bool talker = t < c.world && threadIdx.x < MAX_RANKS * 2 * NV;
+    unsigned got = 0u;
+    if (talker) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[w >> 1]);
+        if (release) __threadfence_system();
+        st_relaxed_sys_u64(&c.peer[t]->ll[slot][c.rank][w], tag | ((w & 1) ? (bits >> 32) : (bits & 0xffffffffull)));
+        unsigned long long v;
+        do { v = ld_relaxed_sys_u64(&c.local->ll[slot][t][w]); } while ((v & 0xffffffff00000000ull) != tag);
+        got = (unsigned)(v & 0xffffffffull);
+        if (!(w & 1)) s_lo[t][w >> 1] = got;
+    }
+    __syncthreads();
+    if (talker && (w & 1))
+        s_part[t][w >> 1] = __longlong_as_double((long long)((unsigned long long)s_lo[t][w >> 1] | ((unsigned long long)got << 32)));
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double total = 0.0;
+        for (int r = 0; r < c.world; r++) total += s_part[r][threadIdx.x];      // rank order: identical bits on every rank
+        vals[threadIdx.x] = total;
+    }
+    if (threadIdx.x == 0) *c.seq = seq;
+    __syncthreads();
 }
 
 // grid_reduce_last + the cross-rank sum: returns true in the last block of every rank with the WORLD total

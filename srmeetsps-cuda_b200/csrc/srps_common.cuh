@@ -49,6 +49,8 @@ struct CgScalars {
     int active;       // r1 > tol^2 && k <= max_iter
     int max_iter;
     float tol2;
+    int plane;        // fused CG: the ping-pong plane that holds the search direction of the pending z step
+    int pad_;
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }

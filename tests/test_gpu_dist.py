@@ -9,7 +9,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_strip_partition_matches_single_gpu():
+@pytest.mark.parametrize("cg", ["graph", "fused"])
+def test_strip_partition_matches_single_gpu(cg):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -17,7 +18,7 @@ def test_strip_partition_matches_single_gpu():
     world = 2
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "dist_strip_check.py")],
-                         capture_output=True, text=True, timeout=900)
+                         capture_output=True, text=True, timeout=900, env=dict(os.environ, SRPS_CG=cg))
     sys.stdout.write(res.stdout[-4000:])
     sys.stderr.write(res.stderr[-4000:])
     assert res.returncode == 0 and "DIST_OK" in res.stdout
