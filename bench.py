@@ -255,27 +255,38 @@ def run_ours(args, rank, world, local):
     h2d = (sc["I"].nbytes + sc["z"].nbytes + sc["z0s"].nbytes) / args.steps
     d2h = sum(v.nbytes for v in out.values()) / args.steps + 16
 
-    # ---- roofline of the dominant kernel (CG stencil), timed alone
+    # ---- roofline of the dominant kernel of the CG driver in use, timed alone
     prof = ctx.profile_kernels(reps=30)
     peak, peak_src = measured_peaks()
-    alg_bytes = 28.0 * npix          # reads r, p, w0..2 ; writes p, y  
-    achieved = alg_bytes / (prof["cg_stencil"] * 1e-3) / 1e9
+    fused = prof["cg_driver"] == "fused"
+    if fused:      # one kernel per pass: reads r, y, p, z, w0..2 ; writes r, p, y, z  
+        kernel = "cg_fused_kernel<sf> (CG pass: r -= alpha y; z += alpha p; p <- r + beta p; y <- (KtK + GtMG) p; r.r, p.y, r.y, y.y)"
+        bytes_px, ms_kernel, tkey = 44.0, prof["cg_fused"], "cg_fused"
+    else:          # operator kernel of the two-kernel form: reads r, p, w0..2 ; writes p, y
+        kernel = "stencil_strip_kernel<MODE_ITER, sf> (CG operator: p <- r + beta p; y <- (KtK + GtMG) p; p.y)"
+        bytes_px, ms_kernel, tkey = 28.0, prof["cg_stencil"], "cg_operator"
+    alg_bytes = bytes_px * npix
+    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get(args.workload, {}).get("cg_operator")
+            traffic = json.load(fh).get(args.workload, {}).get(tkey)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "stencil_strip_kernel<MODE_ITER, sf> (CG operator: p <- r + beta p; y <- (KtK + GtMG) p; p.y)",
+    pass_bytes = 44.0 if fused else 52.0
+    roofline = {"bound": "hbm", "kernel": kernel,
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": prof["cg_stencil"],
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_kernel, "cg_driver": prof["cg_driver"],
                 "other_kernels": {
-                    "cg_update_kernel": {"ms": prof["cg_update"], "GBps": 24.0 * npix / (prof["cg_update"] * 1e-3) / 1e9},
+                    "stencil_strip_kernel (two-kernel form)": {"ms": prof["cg_stencil"], "GBps": 28.0 * npix / (prof["cg_stencil"] * 1e-3) / 1e9},
+                    "cg_update_kernel (two-kernel form)": {"ms": prof["cg_update"], "GBps": 24.0 * npix / (prof["cg_update"] * 1e-3) / 1e9},
+                    "cg_fused_kernel": {"ms": prof["cg_fused"], "GBps": 44.0 * npix / (max(prof["cg_fused"], 1e-9) * 1e-3) / 1e9},
                     "lighting_pass": {"ms": prof["lighting_pass"], "GBps": (4.0 * n * 3 + 24) * npix / (prof["lighting_pass"] * 1e-3) / 1e9},
                     "project_pass": {"ms": prof["project_pass"], "GBps": (4.0 * n * 3 + 72) * npix / (prof["project_pass"] * 1e-3) / 1e9}},
                 "cg_loop_GBps_survey_64B": 64.0 * npix * float(np.mean(cg_iters)) / (float(np.mean(phases["ms_depth_cg"])) * 1e-3) / 1e9,
-                "cg_loop_GBps_actual_52B": 52.0 * npix * float(np.mean(cg_iters)) / (float(np.mean(phases["ms_depth_cg"])) * 1e-3) / 1e9}
+                "cg_loop_GBps_actual": pass_bytes * npix * float(np.mean(cg_iters)) / (float(np.mean(phases["ms_depth_cg"])) * 1e-3) / 1e9,
+                "cg_loop_bytes_per_pixel_pass": pass_bytes}
     ctx.close()
 
     if rank != 0:
@@ -291,11 +302,11 @@ def run_ours(args, rank, world, local):
         "config": {"workload": f"{h}x{w} HR, sf={sf}, {n} images, full mask (BASELINE config {'4' if args.workload == '4k' else '3'})",
                    "albedo": args.albedo, "depth_cg": "reference schedule: un-preconditioned, 101 passes",
                    "parallelism": "1 GPU" if world == 1 else (
-                       f"{world} strips of the same scene along the image columns, 1 ghost line per neighbour + 2 CG scalars per pass "
+                       f"{world} strips of the same scene along the image columns, ghost lines pulled from the neighbours + one 4-value all-reduce per CG pass, "
                        f"exchanged in-kernel over NVLink peer memory" if strips else
                        f"{world} independent replicas, one scene per GPU (value = ms per scene-iteration)"),
-                   "l2": (f"per GPU: image stack {sc['I'].nbytes / 1e9:.2f} GB, CG working set {28 * npix / 1e6:.0f} MB per pass; "
-                          + ("both exceed the 126 MB L2: no flush needed" if 28 * npix > 126e6 else
+                   "l2": (f"per GPU: image stack {sc['I'].nbytes / 1e9:.2f} GB, CG working set {pass_bytes * npix / 1e6:.0f} MB per pass; "
+                          + ("both exceed the 126 MB L2: no flush needed" if pass_bytes * npix > 126e6 else
                              "the stack exceeds the 126 MB L2, the CG vectors fit it (algorithmic GB/s of the CG may exceed the HBM peak)"))},
         "e2e": {"value": e2e_ms if (strips or world == 1) else e2e_ms / world, "unit": "ms",
                 "h2d_bytes_per_step": h2d * (world if strips else 1), "d2h_bytes_per_step": d2h * (world if strips else 1),

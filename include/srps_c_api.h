@@ -136,9 +136,11 @@ int  srps_timer_start(srps_ctx* ctx);
 int  srps_timer_stop(srps_ctx* ctx, float* ms);
 
 /* Measurement hook (bench.py roofline): average device time (ms, cudaEvent on the launching
- * stream) of `reps` back-to-back launches of one kernel alone.  out_ms[0] = CG stencil kernel
+ * stream) of `reps` back-to-back launches of one kernel alone.  out_ms[6]: [0] = CG operator kernel
  * (p <- r + beta p; y <- A p; p.y), [1] = CG update kernel, [2] = lighting stack pass,
- * [3] = stack-projection pass (+ fused albedo / depth coefficients).  Needs one completed
+ * [3] = stack-projection pass (+ fused albedo / depth coefficients), [4] = fused CG pass (operator +
+ * the previous pass's update in one kernel; 0 if sf > 4), [5] = CG driver this context uses
+ * (0 operator + update graph, 1 persistent cooperative kernel, 2 fused pass graph).  Needs one completed
  * srps_outer_iteration; leaves the loop state UNDEFINED (re-upload before further use). */
 int  srps_profile_kernels(srps_ctx* ctx, int reps, float* out_ms);
 

@@ -179,9 +179,10 @@ class Context:
 
     def profile_kernels(self, reps=20):
         """Average device ms of the dominant kernels timed alone (state is undefined afterwards)."""
-        out = (C.c_float * 4)()
+        out = (C.c_float * 6)()
         self._ck(self.lib.srps_profile_kernels(self._ctx, int(reps), out), "srps_profile_kernels")
-        return dict(cg_stencil=out[0], cg_update=out[1], lighting_pass=out[2], project_pass=out[3])
+        return dict(cg_stencil=out[0], cg_update=out[1], lighting_pass=out[2], project_pass=out[3], cg_fused=out[4],
+                    cg_driver={0: "graph", 1: "persistent", 2: "fused"}[int(out[5])])
 
     def apply_depth_operator(self, p):
         p = np.ascontiguousarray(p, dtype=np.float32)

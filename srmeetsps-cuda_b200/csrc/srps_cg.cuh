@@ -58,7 +58,14 @@ struct StencilArgs {
     const float* y_prev_line;              // previous rank's line ny_prev-1 of y_in
     const float* y_next_line;              // next rank's line 0 of y_in
     int plane;                             // which ping-pong plane p_out is (recorded for cg_tail_kernel)
+    int lc_slot;                           // warp-strip kernels: this context's slot of c_lc (constant-bank copy of *lc)
 };
+
+// Constant-bank copies of the per-iteration lighting constants, one slot per live context: the warp-strip kernels take
+// the 18 S3 coefficients of make_qm as constant operands instead of holding them in 18 registers per thread (they run
+// at the 168-register limit of 3 CTAs/SM).  Refreshed by a device-to-device copy whenever *lc changes (srps_api.cu).
+constexpr int LC_SLOTS = 64;
+__constant__ LightConsts c_lc[LC_SLOTS];
 
 struct StencilSmem {
     float P[RL][SP];
@@ -324,6 +331,13 @@ constexpr int SW_NT = 128;       // 4 independent warps per CTA
 constexpr int SW_COLS = 30;      // output float4 columns per warp
 constexpr int SW_G = 4;          // lines per group (multiple of sf)
 
+#ifndef SRPS_ITER_CLC
+#define SRPS_ITER_CLC 0          // two-kernel form: lighting constants from the constant bank (1) or 18 registers (0)
+#endif
+// Rejected (round 1, measured at 4096^2): staging the next group of lines in shared memory with per-lane cp.async copies
+// (global -> shared while the current group is computed, 58 KB per CTA) instead of holding the loads in registers:
+// two-kernel CG 18.2 ms against 15.5 ms, fused CG 16.8-21.3 ms against 14.5 ms -- 36 LDGSTS + 36 LDS per lane and group
+// cost more than the latency they hide.
 struct LineQ { float4 q0f, q0b, q1f, q1b, own; };
 
 __device__ __forceinline__ unsigned ld_types(const unsigned char* t, long long off) {
@@ -359,7 +373,7 @@ __device__ __forceinline__ LineQ line_q(const LightConsts& lc, float fx, float f
 // are the ping-pong planes of this pass; returns this thread's partial of p.y (MODE_ITER).
 template <int MODE, int SF>
 __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightConsts& lc, float beta, float alpha = 0.f,
-                                             double* extra = nullptr /* FUSED: r.r, r.y, y.y */) {
+                                             double* extra = nullptr /* FUSED: r.r, y_in.p, y.y */) {
     static_assert(MODE == MODE_ITER || MODE == MODE_APPLY || MODE == MODE_FUSED || MODE == MODE_FUSED0,
                   "the warp-strip kernel implements ITER, APPLY and the fused pass");
     constexpr bool FUSED = (MODE == MODE_FUSED || MODE == MODE_FUSED0);
@@ -371,7 +385,7 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
     const float inv4 = 1.f / (float)(SF * SF * SF * SF);
     const unsigned FULL = 0xffffffffu;
     const int nitems = a.strip_n * a.strip_chunks;
-    double dot = 0.0, s_rr = 0.0, s_ry = 0.0, s_yy = 0.0;
+    double dot = 0.0, s_rr = 0.0, s_yp = 0.0, s_yy = 0.0;
 
     for (int item = blockIdx.x * (SW_NT / 32) + warp; item < nitems; item += gridDim.x * (SW_NT / 32)) {
         const int strip = item % a.strip_n, chunk = item / a.strip_n;
@@ -405,21 +419,23 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
         };
         // fused pass: the previous pass's residual update is applied on the fly (window AND halo: the halo is recomputed
         // redundantly, like p), rn = r - alpha y_in ; returns p = rn + beta p_in ; pin = p_in (for the z update)
-        auto load_fused = [&](int j, float4& rn, float4& pin) -> float4 {
+        auto load_fused = [&](int j, float4& rn, float4& pin, float& ypn) -> float4 {
             const bool ok = colok && j <= ny;
             const long long off = ok ? (long long)j * pitch + x : 0;
             const float* rs = a.r + off;
             rs = (ok && j < 0 && a.r_prev_line) ? a.r_prev_line + x : rs;
             rs = (ok && j == ny && a.r_next_line) ? a.r_next_line + x : rs;
             const float4 r4 = ldg4(rs);
-            if (MODE == MODE_FUSED0) { rn = r4; pin = f4zero(); return r4; }       // first pass: p = r
+            if (MODE == MODE_FUSED0) { rn = r4; pin = f4zero(); ypn = 0.f; return r4; }       // first pass: p = r
             const float* ys = a.y_in + off;
             ys = (ok && j < 0 && a.y_prev_line) ? a.y_prev_line + x : ys;
             ys = (ok && j == ny && a.y_next_line) ? a.y_next_line + x : ys;
             const float4 y4 = ldg4(ys);
             pin = ldg4(a.p_in + off);
             rn = make_float4(r4.x - alpha * y4.x, r4.y - alpha * y4.y, r4.z - alpha * y4.z, r4.w - alpha * y4.w);
-            return make_float4(rn.x + beta * pin.x, rn.y + beta * pin.y, rn.z + beta * pin.z, rn.w + beta * pin.w);
+            const float4 pn = make_float4(rn.x + beta * pin.x, rn.y + beta * pin.y, rn.z + beta * pin.z, rn.w + beta * pin.w);
+            ypn = (y4.x * pn.x + y4.y * pn.y) + (y4.z * pn.z + y4.w * pn.w);      // (A p_in).p : the conjugacy defect, see cg_fused_kernel
+            return pn;
         };
         // z is read and written by this kernel (each float4 by its owner only): coherent load, clamped like the others
         auto load_x = [&](int j) -> float4 {
@@ -427,13 +443,14 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
             return ld4(a.x + (ok ? (long long)j * pitch + x : 0));
         };
         // owner's stores of a freshly loaded line: the new residual, the pending z step, and r.r
-        auto store_owned = [&](int j, const float4& rn, const float4& xo, const float4& pin) {
+        auto store_owned = [&](int j, const float4& rn, const float4& xo, const float4& pin, float ypn) {
             if (writer && j < jB) {
                 const long long off = (long long)j * pitch + x;
                 st4(a.r_out + off, rn);
                 if (MODE == MODE_FUSED)
                     st4(a.x + off, make_float4(xo.x + alpha * pin.x, xo.y + alpha * pin.y, xo.z + alpha * pin.z, xo.w + alpha * pin.w));
                 s_rr += (double)((rn.x * rn.x + rn.y * rn.y) + (rn.z * rn.z + rn.w * rn.w));
+                s_yp += (double)ypn;
             }
         };
         auto load_t = [&](int j) -> unsigned {
@@ -447,18 +464,18 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
         };
 
         float4 pl[SW_G + 1], wl0[SW_G + 1], wl1[SW_G + 1], wl2[SW_G + 1];
-        float4 rl[SW_G + 1];                    // FUSED: residual window (r.y is formed when y leaves the pipeline)
         unsigned tl[SW_G + 1];
         float4 pprev, q0f_prev;
         {   // prologue: the forward x-rows of line jA-1 reach line jA
             float4 w0, w1, w2;
-            float4 pin0 = f4zero(), x0 = f4zero();
-            if (FUSED) { float4 rdum, pdum; pprev = load_fused(jA - 1, rdum, pdum); } else pprev = load_pn(jA - 1);
+            float4 pin0 = f4zero(), x0 = f4zero(), r0 = f4zero();
+            float yp0 = 0.f;
+            if (FUSED) { float4 rdum, pdum; float ydum; pprev = load_fused(jA - 1, rdum, pdum, ydum); } else pprev = load_pn(jA - 1);
             const unsigned tp = load_t(jA - 1);
             load_w(jA - 1, w0, w1, w2);
-            if (FUSED) { pl[0] = load_fused(jA, rl[0], pin0); if (MODE == MODE_FUSED) x0 = load_x(jA); } else pl[0] = load_pn(jA);
+            if (FUSED) { pl[0] = load_fused(jA, r0, pin0, yp0); if (MODE == MODE_FUSED) x0 = load_x(jA); } else pl[0] = load_pn(jA);
             tl[0] = load_t(jA); load_w(jA, wl0[0], wl1[0], wl2[0]);
-            if (FUSED) store_owned(jA, rl[0], x0, pin0);
+            if (FUSED) store_owned(jA, r0, x0, pin0, yp0);
             const float left = __shfl_up_sync(FULL, pprev.w, 1), right = __shfl_down_sync(FULL, pprev.x, 1);
             const float xx = (float)(g.jb0 + jA - 1) - g.cx;
             const LineQ q = line_q(lc, g.fx, g.fy, xx, yy0, tp & 0xfbfbfbfbu /* backward x-rows not needed */, pprev, f4zero(),
@@ -468,11 +485,12 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
             if (KEEPS_P && a.comm.world > 1 && chunk == 0 && writer) st4(a.p_out - pitch + x, pprev);
         }
         for (int j0 = jA; j0 < jB; j0 += SW_G) {
-            float4 pin[SW_G + 1], xo[SW_G + 1];
+            float4 pin[SW_G + 1], xo[SW_G + 1], rn[SW_G + 1];
+            float ypn[SW_G + 1];
 #pragma unroll
             for (int l = 1; l <= SW_G; l++) {
                 if (FUSED) {
-                    pl[l] = load_fused(j0 + l, rl[l], pin[l]);
+                    pl[l] = load_fused(j0 + l, rn[l], pin[l], ypn[l]);
                     xo[l] = (MODE == MODE_FUSED) ? load_x(j0 + l) : f4zero();
                 } else {
                     pl[l] = load_pn(j0 + l);
@@ -481,7 +499,7 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
             }
             if (FUSED) {                        // after the whole batch of loads: stores inside it would serialise them
 #pragma unroll
-                for (int l = 1; l <= SW_G; l++) store_owned(j0 + l, rl[l], xo[l], pin[l]);
+                for (int l = 1; l <= SW_G; l++) store_owned(j0 + l, rn[l], xo[l], pin[l], ypn[l]);
             }
             if (KEEPS_P && a.comm.world > 1 && j0 + SW_G >= ny && writer) {      // ghost line below: keep p there too
 #pragma unroll
@@ -519,7 +537,7 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
                 const float q1fv[5] = {q1f_left, q.q1f.x, q.q1f.y, q.q1f.z, q.q1f.w};
                 const float q1bv[5] = {q.q1b.x, q.q1b.y, q.q1b.z, q.q1b.w, q1b_right};
                 float4 out;
-                float dl = 0.f, dry = 0.f, dyy = 0.f;
+                float dl = 0.f, dyy = 0.f;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const unsigned t = (tl[l] >> (8 * k)) & 0xffu;
@@ -531,22 +549,21 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
                     if (!(t & T_MASK)) yv = 0.f;
                     f4set(out, k, yv);
                     dl += f4get(pc, k) * yv;
-                    if (FUSED) { dry += f4get(rl[l], k) * yv; dyy += yv * yv; }
+                    if (FUSED) dyy += yv * yv;
                 }
                 if (writer && j < jB) {
                     const long long off = (long long)j * pitch + x;
                     st4(a.y + off, out);
                     if (KEEPS_P) { st4(a.p_out + off, pc); dot += (double)dl; }
-                    if (FUSED) { s_ry += (double)dry; s_yy += (double)dyy; }
+                    if (FUSED) s_yy += (double)dyy;
                 }
                 q0f_prev = q.q0f;
             }
             pprev = pl[SW_G - 1];
             pl[0] = pl[SW_G]; tl[0] = tl[SW_G]; wl0[0] = wl0[SW_G]; wl1[0] = wl1[SW_G]; wl2[0] = wl2[SW_G];
-            if (FUSED) rl[0] = rl[SW_G];
         }
     }
-    if (FUSED) { extra[0] = s_rr; extra[1] = s_ry; extra[2] = s_yy; }
+    if (FUSED) { extra[0] = s_rr; extra[1] = s_yp; extra[2] = s_yy; }
     return dot;
 }
 
@@ -558,7 +575,11 @@ __global__ void __launch_bounds__(SW_NT, SRPS_STRIP_MINB) stencil_strip_kernel(c
         if (!a.sc->active) return;
         beta = a.sc->beta;
     }
+#if SRPS_ITER_CLC
+    const LightConsts& lc = c_lc[a.lc_slot];
+#else
     const LightConsts lc = *a.lc;
+#endif
     const double dot = strip_pass<MODE, SF>(a, lc, beta);
     if (MODE == MODE_APPLY) return;
     double total;
@@ -630,7 +651,10 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_update_kernel(const UpdateArgs a)
 //     r_k = r_{k-1} - alpha_{k-1} y_{k-1}        (window + halo, written to the other r plane)
 //     z  += alpha_{k-1} p_{k-1}
 //     p_k = r_k + beta_k p_{k-1} ,  y_k = A p_k
-// and reduces four dots at once: S0 = r_k.r_k, S1 = p_k.y_k, S2 = r_k.y_k, S3 = y_k.y_k.  Then
+// and reduces four dots at once: S0 = r_k.r_k, S1 = p_k.y_k, S3 = y_k.y_k and C = y_{k-1}.p_k, from which
+//     S2 = r_k.y_k = (p_k - beta_k p_{k-1}).A p_k = S1 - beta_k C        (A symmetric: p_{k-1}.A p_k = y_{k-1}.p_k)
+// -- C is the conjugacy defect of consecutive directions (zero in exact arithmetic), measured where y_{k-1} and p_k are
+// both in registers, so no residual window has to be carried to the point where y_k leaves the pipeline.  Then
 //     alpha_k    = S0 / S1                                   devicecalls.cu:269  (r.r measured, as in the reference)
 //     |r_{k+1}|^2 = S0 - 2 alpha_k S2 + alpha_k^2 S3          (= |r_k - alpha_k y_k|^2 expanded, fp64)
 //     beta_{k+1} = |r_{k+1}|^2 / S0                          devicecalls.cu:262
@@ -686,7 +710,7 @@ __global__ void __launch_bounds__(SW_NT, SRPS_FUSED_MINB) cg_fused_kernel(const 
     if (!a.sc->active) return;
     const float beta = FIRST ? 0.f : a.sc->beta;
     const float alpha = FIRST ? 0.f : a.sc->alpha;          // the step of the previous pass, still pending
-    const LightConsts lc = *a.lc;
+    const LightConsts& lc = c_lc[a.lc_slot];
     double ex[3];
     const double py = strip_pass<FIRST ? MODE_FUSED0 : MODE_FUSED, SF>(a, lc, beta, alpha, ex);
     const double v[4] = {ex[0], py, ex[1], ex[2]};
@@ -694,7 +718,8 @@ __global__ void __launch_bounds__(SW_NT, SRPS_FUSED_MINB) cg_fused_kernel(const 
     peer_allreduce_small<SW_NT, 4>(a.comm, tot, false);
     if (threadIdx.x == 0) {
         CgScalars* s = a.sc;
-        const double S0 = tot[0], S1 = tot[1], S2 = tot[2], S3 = tot[3];
+        const double S0 = tot[0], S1 = tot[1], S3 = tot[3];
+        const double S2 = S1 - (double)beta * tot[2];          // r.y, see the header comment
         if (!((float)S0 > s->tol2)) {            // the reference left its loop before this pass (devicecalls.cu:252)
             s->r1 = S0;
             s->alpha = 0.f;                      // nothing pending: the previous step went into z above
