@@ -30,9 +30,9 @@ if os.path.exists(path):
         a[1] += v
     ours = {k: v for k, v in agg.items() if "srps::" in k or "light_consts" in k}
     tot = sum(v[1] for v in ours.values())
-    out = [f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 700  python bench.py --steps 2 --warmup 1 --no-cpu   (SRPS_NO_GRAPH=1)",
+    out = [f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 600  python bench.py --steps 2 --warmup 1 --no-cpu   (SRPS_NO_GRAPH=1)",
            "# 4096x4096 HR, sf=4, 32 images; cold-cache serialised launch times: compare SHARES, not absolutes.",
-           "# kernels of this library only (the first 700 launches also contain torch's synthetic-scene generation, omitted); shares within the library",
+           "# kernels of this library only (the first 600 launches also contain torch's synthetic-scene generation, omitted); shares within the library",
            "%-72s %6s %12s %7s %10s" % ("kernel", "count", "total_us", "share", "avg_us")]
     for k, (n, t) in sorted(ours.items(), key=lambda kv: -kv[1][1]):
         out.append("%-72s %6d %12.1f %6.1f%% %10.2f" % (k[:72], n, t, 100 * t / tot, t / n))

@@ -1063,7 +1063,7 @@ extern "C" int srps_profile_kernels(srps_ctx* ctx, int reps, float* out_ms) {
         for (int pass = 0; pass < 2; pass++) {
             if (pass == 1) CK(cudaEventRecord(e0, ctx->stream));
             for (int k = 0; k < (pass ? reps : 2); k++) {
-                set_fused_pass(ctx, sf_, k + 1);
+                set_fused_pass(ctx, sf_, k);     // launch 0 reads r, y, p of the last solve; then the planes alternate
                 sf_.x = ctx->dz_new;             // scratch plane: z itself is not touched
                 launch_fused_pass(ctx, sf_, false);
             }
@@ -1074,7 +1074,7 @@ extern "C" int srps_profile_kernels(srps_ctx* ctx, int reps, float* out_ms) {
         out_ms[4] /= reps;
         CK(cudaMemcpyAsync(h + 3, ctx->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        if (!h[3].active) return fail(ctx, SRPS_E_STATE, "profile: the fused CG pass went inactive during the timing loop");
+        if (!h[3].active) out_ms[4] = 0.f;        // the recurrence died on this state: no valid timing (bench.py reports 0)
     }
     out_ms[5] = ctx->use_persistent ? 1.f : (ctx->use_fused ? 2.f : 0.f);
     // restore the reference CG parameters
