@@ -178,6 +178,43 @@ def cg_reference(matvec, x, b, dt=np.float32, max_iter=CG_MAX_ITER, tol=CG_TOL):
     return x, k
 
 
+def cg_fused_reference(matvec, x, b, dt=np.float32, max_iter=CG_MAX_ITER, tol=CG_TOL):
+    """The recurrence of the CUDA path's one-kernel-per-pass CG (csrc/srps_cg.cuh: cg_fused_kernel), restated to
+    show that it is the reference's CG (cg_reference above, devicecalls.cu:229-279) in another order of operations:
+    pass k first applies the step of pass k-1 (r -= alpha y, x += alpha p), then forms p and y = A p and four dots;
+    alpha_k = r.r / p.y with r.r MEASURED; beta_{k+1} = |r_{k+1}|^2 / r.r with |r_{k+1}|^2 = |r - alpha y|^2 expanded
+    from the dots, r.y = p.y - beta (y_prev . p) (A symmetric).  A pass that measures r.r <= tol^2 is void."""
+    f64 = np.float64
+    x = x.astype(dt).copy()
+    r = b.astype(dt).copy()
+    tol2 = dt(tol) * dt(tol)
+    k = 0
+    alpha = dt(0); beta = dt(0)
+    p = np.zeros_like(r); y = np.zeros_like(r)
+    active = dt(np.dot(r.astype(f64), r.astype(f64))) > tol2
+    while active:
+        r = (r - alpha * y).astype(dt)
+        x = (x + alpha * p).astype(dt)
+        y_prev = y
+        p = (r + beta * p).astype(dt)
+        y = matvec(p).astype(dt)
+        S0 = float(np.dot(r.astype(f64), r.astype(f64)))
+        S1 = float(np.dot(p.astype(f64), y.astype(f64)))
+        S3 = float(np.dot(y.astype(f64), y.astype(f64)))
+        C = float(np.dot(y_prev.astype(f64), p.astype(f64)))
+        if not (dt(S0) > tol2):          # the reference left its loop before this pass
+            alpha = dt(0)
+            break
+        alpha = dt(dt(S0) / dt(S1))
+        S2 = S1 - float(beta) * C
+        rr = S0 - 2.0 * float(alpha) * S2 + float(alpha) ** 2 * S3
+        beta = dt(dt(rr) / dt(S0))
+        k += 1
+        active = k <= max_iter
+    x = (x + alpha * p).astype(dt)     # the step still pending after the last pass (cg_tail_kernel)
+    return x, k
+
+
 # --------------------------------------------------------------------------------------
 # Lighting                                                    devicecalls.cu:376-444
 # --------------------------------------------------------------------------------------

@@ -1,13 +1,16 @@
-// Depth update: matrix-free operator  y = (Kt K + G^T M G) p  and the two fused CG kernels.
+// Depth update: matrix-free operator  y = (Kt K + G^T M G) p  and the CG drivers built on it.
 //
 // Replaces, for the depth solve of the reference (SRmeetsPS-GPU/devicecalls.cu:636-786):
 //   * the assembly of A (c*n*npix rows) by 6 SpGEMM + 6 SpGEAM + csr2csc, KtK and AtA by two
 //     more SpGEMM (:668-736)                       -> nothing is assembled; M_p is rebuilt per
 //                                                     pixel from w_c = (rho_c/dz)^2 (12 B/pixel)
-//   * cusparseScsrmv inside the CG (:267)          -> stencil_kernel<MODE_ITER>
-//   * cublasSscal/Saxpy/Sdot/Scopy (:251-274)      -> fused into stencil_kernel / cg_update_kernel
+//   * cusparseScsrmv inside the CG (:267)          -> the stencil (strip_pass / stencil_kernel)
+//   * cublasSscal/Saxpy/Sdot/Scopy (:251-274)      -> fused into the same kernels
 //   * the host-side loop control with 3 blocking dots per pass -> device-resident CgScalars
-// CG recurrences are exactly those of devicecalls.cu:252-275.
+// Three drivers run the reference's CG (devicecalls.cu:229-279: same alpha, beta, stop rule and pass count):
+//   cg_fused_kernel       one kernel + one reduction per pass (default; sf <= 4)
+//   stencil_*_kernel<MODE_ITER> + cg_update_kernel   the textbook two-kernel pass (SRPS_CG=graph; sf 8, 16)
+//   cg_persistent_kernel  every pass of a solve in one cooperative launch (small single-GPU scenes)
 #pragma once
 #include "srps_comm.cuh"
 

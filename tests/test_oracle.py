@@ -118,3 +118,28 @@ def test_mitten_snapshot_matches_survey_anchors(mitten_scene):
         e, k, _ = pt.outer_iteration(stp)
         assert k == 101
         assert abs(e - anchors[it]) < 2e-4 * anchors[it]
+
+
+@pytest.mark.parametrize("cfg", [dict(h=96, w=128, sf=4, n=8, seed=1, mask_kind="ellipse"),
+                                 dict(h=128, w=96, sf=2, n=6, seed=3, mask_kind="random95"),
+                                 dict(h=40, w=24, sf=1, n=6, seed=5, mask_kind="random95")],
+                         ids=lambda c: f"{c['h']}x{c['w']}sf{c['sf']}{c['mask_kind']}")
+def test_fused_cg_recurrence_is_the_reference_cg(cfg):
+    """The one-kernel-per-pass CG of the CUDA path (oracle.cg_fused_reference restates its recurrence) against the
+    reference's CG on the fp32 depth system: same pass count (101, or the early stop of the sf = 1 scene) and a
+    solution within fp32 round-off of it -- closer than the fp64-vector run of the reference recurrence is."""
+    sc = o.synth_scene(**cfg)
+    ops = o.build_operators(sc["mask"], sc["sf"])
+    st = o.init_state(sc["I"], sc["z"], sc["z0s"], ops, sc["K"])
+    s = o.lighting_update(st["s"], st["rho"], st["N"], st["I"])
+    rho, _ = o.albedo_update(s, st["rho"], st["N"], st["I"], closed_form=True)
+    _, _, _, aux = o.depth_update_matfree(s, rho, st["I"], st["xx"], st["yy"], st["dz"], ops, st["z0s"], st["z"],
+                                          st["fx"], st["fy"], dt=np.float32)
+    Aop, rhs = aux["Aop"], aux["rhs"]
+    res = (rhs - Aop(st["z"].astype(np.float32))).astype(np.float32)
+    z_ref, k_ref = o.cg_reference(Aop, st["z"], res, np.float32)
+    z_fus, k_fus = o.cg_fused_reference(Aop, st["z"], res, np.float32)
+    z_f64, _ = o.cg_reference(Aop, st["z"], res, np.float64)
+    assert k_fus == k_ref
+    assert rel_rmse(z_fus, z_ref) <= 5e-7
+    assert rel_rmse(z_fus, z_ref) <= 2.0 * rel_rmse(z_f64.astype(np.float32), z_ref) + 1e-9
