@@ -63,6 +63,7 @@ struct srps_ctx {
     int tiles_x = 0, tiles_y = 0;
     int use_strip = 0, strip_n = 0, strip_chunks = 0, strip_cl = 0, grid_strip = 0;
     int use_persistent = 0, grid_persistent = 0;      // all CG passes in one cooperative launch
+    int use_persistent_fused = 0;                     // ... in the fused form (one grid barrier per pass; opt-in)
     int use_fused = 0;                                // one kernel per CG pass (cg_fused_kernel)
     int lc_slot = -1;                                 // this context's slot of the constant-bank lighting constants (c_lc)
     unsigned long long* sync_words = nullptr;         // [0] grid barrier counter, [1] world generation, [2..5] world totals (as double)
@@ -352,14 +353,20 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, cg_persistent_kernel<4>, SW_NT, 0));
         const char* cgm = getenv("SRPS_CG");
-        // Measured (round 1): the persistent form wins on small single-GPU scenes (Mitten 1.41 vs 1.52 ms, 1080p 2.74 vs
-        // 2.95 ms per outer iteration: fewer, cheaper synchronisation points), loses at 4096^2 (its update phase runs on the
-        // operator's 128-thread blocks: 17.7 vs 15.4 ms) and does not help the strip partition (2 GPUs: 11.9 vs 10.2 ms).
-        // Default: persistent below 3 M pixels on one GPU; SRPS_CG=persistent|graph overrides.
-        const bool want = ctx->world == 1 && (cgm ? strcmp(cgm, "persistent") == 0 : npix < 3000000);
-        ctx->use_persistent = ctx->use_strip && coop && occ_p > 0 && want;
-        // Otherwise one fused kernel per pass (cg_fused_kernel; measured round 1 at 4096^2: 14.5 ms against 15.5 ms for
-        // operator + update, and one cross-GPU reduction per pass instead of two); SRPS_CG=graph keeps the two-kernel form.
+        // Measured (round 1): a persistent single-launch CG wins on small single-GPU scenes (two-barrier form: Mitten 1.35 vs
+        // 1.52 ms, 1080p 2.62 vs 2.95 ms per outer iteration; fused one-barrier form: Mitten 1.11 ms), loses at 4096^2
+        // (17.7 vs 15.4 ms of CG) and does not help the strip partition (2 GPUs: 11.9 vs 10.2 ms).
+        // Default: below 3 M pixels on one GPU the persistent fused form (cg_persistent_fused_kernel), otherwise one fused
+        // kernel per pass (cg_fused_kernel; 4096^2: 14.1 ms against 15.5 ms for operator + update, and one cross-GPU
+        // reduction per pass instead of two).  SRPS_CG = persistent_fused | persistent | fused | graph overrides.
+        const bool small = ctx->world == 1 && npix < 3000000;
+        const bool want_pf = cgm ? strcmp(cgm, "persistent_fused") == 0 : small;
+        const bool want_p = cgm && strcmp(cgm, "persistent") == 0;
+        ctx->use_persistent = ctx->use_strip && coop && occ_p > 0 && ctx->world == 1 && want_p;
+        if (want_pf && ctx->world == 1 && ctx->use_strip && coop) {
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, cg_persistent_fused_kernel<4>, SW_NT, 0));
+            ctx->use_persistent_fused = ctx->use_persistent = occ_p > 0;
+        }
         ctx->use_fused = ctx->use_strip && !ctx->use_persistent && !(cgm && strcmp(cgm, "graph") == 0);
         ctx->grid_persistent = std::min(ctx->grid_strip, ctx->sm_count * std::max(1, occ_p));
         CK(cudaMalloc(&ctx->sync_words, 8 * sizeof(unsigned long long)));
@@ -378,7 +385,7 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, normals_energy_kernel<true>, EP_NT, 0));
     ctx->grid_ep = (int)std::min<long long>((ctx->n4 + EP_NT - 1) / EP_NT, (long long)ctx->sm_count * std::max(1, occ));
     ctx->grid_al = (int)std::min<long long>((ctx->n4 + AL_NT - 1) / AL_NT, (long long)ctx->sm_count * 4);
-    long long pl = std::max<long long>({(long long)ctx->grid_stencil, 4ll * ctx->grid_strip, (long long)ctx->grid_update, (long long)ctx->grid_ep,
+    long long pl = std::max<long long>({(long long)ctx->grid_stencil, 8ll * ctx->grid_strip, (long long)ctx->grid_update, (long long)ctx->grid_ep,
                                         3ll * ctx->grid_al, 30ll * ctx->grid_gram,
                                         (long long)LIGHT_IB * 12 * ctx->grid_light_x * ctx->light_groups}) + 64;
     ctx->partials_len = pl;
@@ -838,11 +845,15 @@ extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
         pa.st = sa; pa.pp[0] = ctx->p; pa.pp[1] = ctx->p2; pa.x = ctx->z; pa.r = ctx->r; pa.n4 = ctx->n4;
         pa.passes = passes;
         pa.bar = ctx->sync_words; pa.world_gen = ctx->sync_words + 1; pa.world_tot = (double*)(ctx->sync_words + 2);
-        pa.part[0] = ctx->partials; pa.part[1] = ctx->partials + ctx->grid_persistent;
+        pa.rr[0] = ctx->r; pa.rr[1] = ctx->r2; pa.yy[0] = ctx->y; pa.yy[1] = ctx->y2;
+        pa.part[0] = ctx->partials; pa.part[1] = ctx->partials + 4ll * ctx->grid_persistent;
         CK(cudaMemsetAsync(ctx->sync_words, 0, 2 * sizeof(unsigned long long), ctx->stream));
         void* kargs[] = {&pa};
         const void* fn = ctx->g.sf == 1 ? (const void*)cg_persistent_kernel<1>
                          : (ctx->g.sf == 2 ? (const void*)cg_persistent_kernel<2> : (const void*)cg_persistent_kernel<4>);
+        if (ctx->use_persistent_fused)
+            fn = ctx->g.sf == 1 ? (const void*)cg_persistent_fused_kernel<1>
+                 : (ctx->g.sf == 2 ? (const void*)cg_persistent_fused_kernel<2> : (const void*)cg_persistent_fused_kernel<4>);
         CK(cudaLaunchCooperativeKernel(fn, dim3(ctx->grid_persistent), dim3(SW_NT), kargs, 0, ctx->stream));
         ctx->launches++;
     } else if (getenv("SRPS_TRACE")) {

@@ -119,3 +119,31 @@ def test_python_srps_class_runs_execute(tmp_path):
     text = out.getvalue()
     assert "Small mask calculation" in text and "Iteration 01 summary" in text and text.rstrip().endswith("Done!")
     assert 1 <= len(s.history) <= 11 and np.isfinite(res["z"]).all() and res["N"].shape[0] == 4
+
+
+def test_many_contexts_share_the_constant_bank_slots():
+    """Every live context owns one slot of the constant-bank lighting constants (64 per process): slots are released on
+    destroy, the 65th live context is refused with a clear message, and two interleaved contexts with different lighting
+    do not see each other's constants."""
+    from srmeetsps_cuda_b200 import Context, SRPSError
+    mask = np.ones((16, 16), np.uint8)
+    K = [20, 0, 0, 0, 20, 0, 7.5, 7.5, 1]
+    for _ in range(70):                                   # sequential create/destroy: slots are reused
+        Context(mask, 4, 2, K).close()
+    held = [Context(mask, 4, 2, K) for _ in range(64)]
+    try:
+        with pytest.raises(SRPSError, match="64 live contexts"):
+            Context(mask, 4, 2, K)
+    finally:
+        for c in held:
+            c.close()
+    # interleaving: A and B hold different scenes; running B between A's phases must not change A's result
+    sa = o.synth_scene(32, 48, 2, 6, seed=31, mask_kind="ellipse")
+    sb = o.synth_scene(32, 48, 2, 6, seed=32, mask_kind="ellipse")
+    with Context(sa["mask"], sa["n"], sa["sf"], sa["K"]) as a, Context(sa["mask"], sa["n"], sa["sf"], sa["K"]) as a2, \
+            Context(sb["mask"], sb["n"], sb["sf"], sb["K"]) as b:
+        for c, s in ((a, sa), (a2, sa), (b, sb)):
+            c.upload_state(s["I"], s["z"], s["z0s"])
+        a.outer_iteration()                               # alone
+        a2.lighting(); b.lighting(); a2.albedo(); b.albedo(); b.depth(); a2.depth(); a2.normals()
+        assert np.array_equal(a.download("z"), a2.download("z"))

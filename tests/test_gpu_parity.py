@@ -165,18 +165,19 @@ def test_outer_iterations_match_oracle(cfg, albedo_mode):
     ctx.close()
 
 
-@pytest.mark.parametrize("stencil", ["persistent", "strip", "tile", "fused"])
+@pytest.mark.parametrize("stencil", ["persistent", "strip", "tile", "fused", "persistent_fused"])
 @pytest.mark.parametrize("albedo_mode", ["closed_form", "reference_cg"])
 @pytest.mark.parametrize("cfg", SCENES, ids=lambda c: f"{c['h']}x{c['w']}sf{c['sf']}{c['mask_kind']}")
 def test_each_iteration_from_synchronised_state(cfg, albedo_mode, stencil, monkeypatch):
     """Sharp per-iteration parity: before every outer iteration the CUDA state is set to the oracle's
     (s, rho, z -> normals), so nothing accumulates; one pass of the loop body must then agree to
     fp32 round-off: depth rel. RMSE <= 2e-5, albedo max-abs <= 3e-4, energy 2e-3, same CG pass count.
-    Four CG drivers: one persistent cooperative kernel per solve (default on small scenes), the two-kernel CUDA graph
-    with the warp-strip operator, the same with the shared-memory tile operator, and the fused one-kernel-per-pass form
-    (sf 8/16 scenes fall back to the tile operator in every case)."""
+    Five CG drivers: one persistent cooperative kernel per solve (default on small scenes), the two-kernel CUDA graph
+    with the warp-strip operator, the same with the shared-memory tile operator, the fused one-kernel-per-pass form
+    (default on large scenes) and the fused form inside one cooperative launch (sf 8/16 scenes fall back to the tile
+    operator in every case)."""
     monkeypatch.setenv("SRPS_STENCIL", "tile" if stencil == "tile" else "strip")
-    monkeypatch.setenv("SRPS_CG", {"persistent": "persistent", "fused": "fused"}.get(stencil, "graph"))
+    monkeypatch.setenv("SRPS_CG", stencil if stencil in ("persistent", "fused", "persistent_fused") else "graph")
     sc = scene(cfg)
     ctx = make_ctx(sc, albedo_mode=albedo_mode)
     st = oracle_state(sc)
