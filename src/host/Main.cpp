@@ -6,6 +6,7 @@
 #include <map>
 #include <string>
 
+#include "../../include/srps_snapshot.h"
 #include "SRPS.h"
 #include "Utilities.h"
 
@@ -17,7 +18,8 @@ static void printMessage() {
                  "\t-t, --dstype (value:matlab)\n\t\tdataset type, can be matlab or images (extension: snapshot)\n"
                  "\t-x, --blockx (value:256)\n\t\tblock dimension x\n"
                  "\t-y, --blocky (value:4)\n\t\tblock dimension y\n"
-                 "\textensions: --albedo=closed_form|reference_cg  --iters=K  --init-only  --dump-init=F.snap  --out=F.snap\n";
+                 "\textensions: --albedo=closed_form|reference_cg  --iters=K  --init-only  --dump-init=F.snap  --out=F.snap\n"
+                 "\t            --outdir=DIR (s/rho/z/N.mat + normals/albedo/depth.png)  --render=F.snap (files from a result snapshot, no GPU)\n";
 }
 
 int main(int argc, char* argv[]) {
@@ -34,6 +36,20 @@ int main(int argc, char* argv[]) {
         if (alias.count(key)) key = alias[key];
         opt[key] = val;
     }
+    if (opt.count("render") && opt.count("outdir")) {        // extension: files from a result snapshot (--out), CPU only
+        try {
+            const srps::Snapshot r = srps::Snapshot::load(opt["render"]);
+            const int32_t* hw = (const int32_t*)r.at("hw").raw.data();
+            const size_t npix = r.at("z").count();
+            save_results(opt["outdir"], hw[0], hw[1], r.at("mask").raw.data(), npix, (int)r.at("s").dims[0],
+                         (const float*)r.at("z").raw.data(), (const float*)r.at("rho").raw.data(),
+                         (const float*)r.at("N").raw.data(), (const float*)r.at("s").raw.data());
+        } catch (const std::exception& e) {
+            std::cerr << e.what() << std::endl;
+            return 1;
+        }
+        return 0;
+    }
     if (opt.count("help") || !opt.count("dsloc")) {          // Main.cpp:19-26
         printMessage();
         return 0;
@@ -46,6 +62,7 @@ int main(int argc, char* argv[]) {
         s.init_only = opt.count("init-only") != 0;
         if (opt.count("dump-init")) s.dump_init = opt["dump-init"];
         if (opt.count("out")) s.dump_result = opt["out"];
+        if (opt.count("outdir")) s.dump_dir = opt["outdir"];
         if (opt.count("iters")) s.fixed_iters = atoi(opt["iters"].c_str());
     };
     try {

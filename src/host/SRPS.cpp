@@ -113,19 +113,26 @@ void SRPS::execute() {
     } while (!stop_loop);
     std::cout << "Done!" << std::endl;                                                            // SRPS.cu:337
 
-    if (!dump_result.empty()) {
+    if (!dump_result.empty() || !dump_dir.empty()) {
         const size_t npix = st.z.size();
         std::vector<float> z(npix), rho(3 * npix), N(4 * npix), s((size_t)st.n * 12);
         if (srps_download(ctx, SRPS_BUF_Z, z.data()) || srps_download(ctx, SRPS_BUF_RHO, rho.data()) ||
             srps_download(ctx, SRPS_BUF_N, N.data()) || srps_download(ctx, SRPS_BUF_S, s.data()))
             die(ctx, "srps_download");
-        srps::Snapshot out;
-        out.put("z", 0, {(int64_t)npix}, z.data());
-        out.put("rho", 0, {3, (int64_t)npix}, rho.data());
-        out.put("N", 0, {4, (int64_t)npix}, N.data());
-        out.put("s", 0, {st.n, 3, 4}, s.data());
-        out.put("energy", 0, {(int64_t)energies.size()}, energies.data());
-        out.save(dump_result);
+        if (!dump_result.empty()) {
+            srps::Snapshot out;
+            const int32_t hw[2] = {st.h, st.w};
+            out.put("hw", 1, {2}, hw);
+            out.put("mask", 2, {(int64_t)st.w, (int64_t)st.h}, st.mask.data());       // column-major h x w
+            out.put("z", 0, {(int64_t)npix}, z.data());
+            out.put("rho", 0, {3, (int64_t)npix}, rho.data());
+            out.put("N", 0, {4, (int64_t)npix}, N.data());
+            out.put("s", 0, {st.n, 3, 4}, s.data());
+            out.put("energy", 0, {(int64_t)energies.size()}, energies.data());
+            out.save(dump_result);
+        }
+        if (!dump_dir.empty())                                                          // SRPS.cu:319-333, as files
+            save_results(dump_dir, st.h, st.w, st.mask.data(), npix, st.n, z.data(), rho.data(), N.data(), s.data());
     }
     srps_ctx_destroy(ctx);
 }

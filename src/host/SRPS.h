@@ -19,7 +19,8 @@ public:
     // extensions (the reference only shows GUI windows and writes nothing on Linux)
     bool init_only = false;               // stop after the one-shot init
     std::string dump_init;                // write the post-init loop state (SRPSNAP1)
-    std::string dump_result;              // write z, rho, N, s and the energies (SRPSNAP1)
+    std::string dump_result;              // write z, rho, N, s, the mask and the energies (SRPSNAP1)
+    std::string dump_dir;                 // write s/rho/z/N.mat and normals/albedo/depth.png there (Output.cpp)
     int fixed_iters = 0;                  // > 0: ignore the stop rule
     std::vector<float> energies;          // per outer iteration, filled by execute()
 };

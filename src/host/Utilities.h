@@ -74,3 +74,13 @@ std::vector<std::string> list_sorted(const std::string& dir);                   
 // zs: inpainted + smoothed LR depth (column-major hs x ws), z_full: bicubic upsample (column-major h x w).
 void preprocess_depth(const float* z0, int z0_h, int z0_w, int z0_n, int I_h, int I_w,
                       std::vector<float>& zs, std::vector<float>& z_full);
+
+// ---- result output (Output.cpp), SRPS.cu:319-333 + Utilities.cpp:242-320 without OpenCV / matio ----------
+// mask: h*w column-major {0,1}; z[npix], rho[3][npix], N[4][npix], s[n][3][4] in the reference's masked layouts.
+void write_png_rgb8(const std::string& path, int w, int h, const unsigned char* rgb);
+void write_mat5_vector(const std::string& path, const float* x, size_t n);
+std::vector<unsigned char> render_normals(int h, int w, const unsigned char* mask, size_t npix, const float* N);
+std::vector<unsigned char> render_albedo(int h, int w, const unsigned char* mask, size_t npix, const float* rho);
+std::vector<unsigned char> render_depth(int h, int w, const unsigned char* mask, size_t npix, const float* z);
+void save_results(const std::string& dir, int h, int w, const unsigned char* mask, size_t npix, int n_images,
+                  const float* z, const float* rho, const float* N, const float* s);

@@ -1,5 +1,6 @@
 """CLI with the reference's flags (Main.cpp:10-17): --dstype/-t, --dsloc/-d, --device/-g,
---blockx/-x, --blocky/-y, --help/-h/--usage, `--key=value` syntax."""
+--blockx/-x, --blocky/-y, --help/-h/--usage, `--key=value` syntax.  Extensions: --albedo=closed_form|reference_cg,
+--outdir=DIR (result dumps and renderings, output.py)."""
 import sys
 
 from .srps import ImageDataHandler, MatFileDataHandler, Preferences, SRPS
@@ -45,10 +46,10 @@ def main(argv=None):
         Preferences.albedo_mode = opts["albedo"]
     if opts["dstype"] == "matlab":                   # Main.cpp:31-36
         dh = MatFileDataHandler().loadDataFromMatFiles(opts["dsloc"])
-        SRPS(dh).execute()
+        SRPS(dh).execute(out_dir=opts.get("outdir"))
     elif opts["dstype"] == "images":                 # Main.cpp:37-42
         dh = ImageDataHandler().loadDataFromImages(opts["dsloc"])
-        SRPS(dh).execute()
+        SRPS(dh).execute(out_dir=opts.get("outdir"))
     return 0                                         # any other dstype: silently nothing (Main.cpp:43)
 
 

@@ -111,7 +111,9 @@ class SRPS:                             # SRPS.h:10-18
         self.history = []
         self.result = None
 
-    def execute(self, out=sys.stdout):
+    def execute(self, out=sys.stdout, out_dir=None):
+        """SRPS::execute (SRPS.cu:84-349).  out_dir (extension): write the reference's dumps and renderings there
+        (output.save_results: s/rho/z/N.mat, normals/albedo/depth.png) instead of opening windows (SRPS.cu:319-333)."""
         dh = self.dh
         TOLERANCE, MAX_ITERATIONS = 5e-3, 10                       # SRPS.cu:85-86
         h, w, sf = dh.I_h, dh.I_w, int(dh.sf)
@@ -160,4 +162,7 @@ class SRPS:                             # SRPS.h:10-18
         self.result = dict(z=ctx.download("z"), rho=ctx.download("rho"), N=ctx.download("N"), s=ctx.download("s"),
                            mask=mask)
         ctx.close()
+        if out_dir:
+            from .output import save_results
+            save_results(self.result, out_dir)
         return self.result

@@ -127,8 +127,11 @@ def test_cli_loop_matches_python_host(cli, tmp_path, mitten_scene):
     write_snapshot(snap_in, {"dims": np.array([sc["h"], sc["w"], sc["sf"]], np.int32), "K": np.asarray(sc["K"], np.float32),
                              "mask": (sc["mask"] != 0).astype(np.uint8).ravel(order="F"), "I": sc["I"], "z": sc["z"], "z0s": sc["z0s"]})
     out = str(tmp_path / "res.snap")
-    res = subprocess.run([cli, "--dstype=snapshot", f"--dsloc={snap_in}", "--iters=3", f"--out={out}"], capture_output=True, text=True)
+    files = str(tmp_path / "files")
+    res = subprocess.run([cli, "--dstype=snapshot", f"--dsloc={snap_in}", "--iters=3", f"--out={out}", f"--outdir={files}"],
+                         capture_output=True, text=True)
     assert res.returncode == 0, res.stderr + res.stdout
+    assert sorted(os.listdir(files)) == ["N.mat", "albedo.png", "depth.png", "normals.png", "rho.mat", "s.mat", "z.mat"]
     assert "Iteration 03 summary" in res.stdout and "Lightning Estimation" in res.stdout          # SRPS.cu:283,303
     r = read_snapshot(out)
     with Context(sc["mask"], sc["n"], sc["sf"], sc["K"]) as ctx:
@@ -136,3 +139,32 @@ def test_cli_loop_matches_python_host(cli, tmp_path, mitten_scene):
         e = [ctx.outer_iteration()[0] for _ in range(3)]
         assert np.array_equal(np.asarray(e, np.float32), r["energy"])
         assert np.array_equal(ctx.download("z"), r["z"])
+
+
+def test_result_files_match_python_output(cli, tmp_path):
+    """N4: `srps_cli --render=result.snap --outdir=DIR` (the files `--outdir` writes after a run) against
+    srmeetsps_cuda_b200.output on the same result: MAT vectors and the normals / depth PNGs byte-identical, the albedo
+    PNG within one level (its cap uses an fp32 mean whose summation order differs)."""
+    import cv2
+    import scipy.io
+    from srmeetsps_cuda_b200 import output
+    from srmeetsps_cuda_b200.snapshot import write_snapshot
+    from test_output import _scene
+    r = _scene(h=40, w=56, seed=11)
+    h, w = r["mask"].shape
+    snap = str(tmp_path / "result.snap")
+    write_snapshot(snap, dict(hw=np.array([h, w], np.int32), mask=np.ascontiguousarray(r["mask"].T.astype(np.uint8)),
+                              z=r["z"], rho=r["rho"], N=r["N"], s=r["s"], energy=np.zeros(1, np.float32)))
+    d_cpp, d_py = str(tmp_path / "cpp"), str(tmp_path / "py")
+    res = subprocess.run([cli, f"--render={snap}", f"--outdir={d_cpp}"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    output.save_results(r, d_py)
+    for name in ("s", "rho", "z", "N"):
+        a = scipy.io.loadmat(os.path.join(d_cpp, name + ".mat"))["x"]
+        b = scipy.io.loadmat(os.path.join(d_py, name + ".mat"))["x"]
+        assert a.dtype == np.float32 and np.array_equal(a, b)
+    for name, tol in (("normals", 0), ("depth", 0), ("albedo", 1)):
+        a = cv2.imread(os.path.join(d_cpp, name + ".png"), cv2.IMREAD_COLOR)
+        b = cv2.imread(os.path.join(d_py, name + ".png"), cv2.IMREAD_COLOR)
+        assert a is not None and a.shape == b.shape == (h, w, 3)
+        assert np.abs(a.astype(int) - b.astype(int)).max() <= tol, name
