@@ -168,3 +168,16 @@ def test_result_files_match_python_output(cli, tmp_path):
         b = cv2.imread(os.path.join(d_py, name + ".png"), cv2.IMREAD_COLOR)
         assert a is not None and a.shape == b.shape == (h, w, 3)
         assert np.abs(a.astype(int) - b.astype(int)).max() <= tol, name
+
+
+def test_images_to_mat_round_trip(tmp_path):
+    """BASELINE config 1 substitute: the image folder re-encoded as MAT v5 loads to the same DataHandler (python host)."""
+    from srmeetsps_cuda_b200 import ImageDataHandler, MatFileDataHandler
+    from srmeetsps_cuda_b200.images_to_mat import images_to_mat
+    folder = write_image_folder(str(tmp_path / "scene"))
+    path = images_to_mat(folder, str(tmp_path / "scene.mat"))
+    a = ImageDataHandler().loadDataFromImages(folder)
+    b = MatFileDataHandler().loadDataFromMatFiles(path)
+    assert (a.I_h, a.I_w, a.I_c, a.I_n, int(a.sf), a.z0.shape) == (b.I_h, b.I_w, b.I_c, b.I_n, int(b.sf), b.z0.shape)
+    assert np.array_equal(a.I, b.I) and np.array_equal(a.K, b.K) and np.array_equal(a.z0, b.z0)
+    assert np.array_equal(a.mask != 0, b.mask != 0)
