@@ -7,7 +7,7 @@ for cfg in [dict(h=64, w=96, sf=2, n=6, seed=12, mask_kind="random95"), dict(h=3
             dict(h=48, w=272, sf=8, n=6, seed=6, mask_kind="ellipse"), dict(h=40, w=24, sf=1, n=6, seed=5, mask_kind="random95")]:
     sc = o.synth_scene(cfg["h"], cfg["w"], cfg["sf"], cfg["n"], seed=cfg["seed"], mask_kind=cfg["mask_kind"])
     for mode in ("closed_form", "reference_cg"):
-        for stencil, cg in (("strip", "persistent"), ("strip", "graph"), ("strip", "fused"), ("tile", "graph")):
+        for stencil, cg in (("strip", "persistent_fused"), ("strip", "persistent"), ("strip", "graph"), ("strip", "fused"), ("tile", "graph")):
             os.environ["SRPS_STENCIL"] = stencil
             os.environ["SRPS_CG"] = cg
             with Context(sc["mask"], sc["n"], sc["sf"], sc["K"], albedo_mode=mode, cg_max_iter=5) as ctx:
