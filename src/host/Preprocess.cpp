@@ -4,8 +4,8 @@
 // upsampling.  Like the reference, every step runs on the TRANSPOSED low-resolution image (the reference wraps its
 // column-major buffer in a cv::Mat(z0_w rows, z0_h cols), SRPS.cu:130-132) -- for these isotropic filters that
 // only fixes the memory order.  This is host init ("next" row N2 of SURVEY §8f), off the hot path: it follows the
-// published algorithms (Telea 2004; Tomasi-Manduchi; Keys cubic convolution as OpenCV parametrises it), it is not
-// bit-identical to OpenCV 3.3 -- tests/test_cpp_host.py bounds the difference against python cv2 on Mitten.
+// published algorithms (Telea 2004; Tomasi-Manduchi; Keys cubic convolution) in OpenCV's parametrisation and agrees
+// with python cv2 to a few ulp (tests/test_cpp_host.py: synthetic scenes with depth drop-outs and Mitten).
 #include <algorithm>
 #include <cmath>
 #include <queue>
@@ -16,134 +16,163 @@
 namespace {
 
 // ---- Telea inpainting on a rows x cols float image (row-major) -------------------------------------------------
-enum : unsigned char { KNOWN = 0, BAND = 1, INSIDE = 2 };
+// Fast-marching inpainting (A. Telea, "An image inpainting technique based on the fast marching method", 2004) in the
+// parametrisation of cv::inpaint(src, mask, dst, range, INPAINT_TELEA), which is what the reference calls
+// (SRPS.cu:133): a one-pixel frame around the image, flags KNOWN / BAND / INSIDE, a stable priority queue (ties
+// leave in insertion order), the arrival time T marched outwards over the (2 range + 1)-square dilation of the hole
+// first (negated: it gives grad T a meaning on the known side), then inwards; every new pixel is the weighted mean of
+// the known pixels within `range` with weight |dir * dst * lev| (dst = 1/|r|^3, lev = 1/(1 + |T_q - T_p|),
+// dir = r . grad T, floored at 1e-6) plus the normalised first-order term, one-sided differences next to unknown
+// pixels, single-precision accumulators.  tests/test_cpp_host.py holds it to python cv2 within a few ulp.
+enum : unsigned char { KNOWN = 0, BAND = 1, INSIDE = 2, CHANGE = 3 };
 
-struct HeapItem { float t; int idx; bool operator>(const HeapItem& o) const { return t > o.t; } };
-using MinHeap = std::priority_queue<HeapItem, std::vector<HeapItem>, std::greater<HeapItem>>;
+struct HeapItem {
+    float t; unsigned seq; int i, j;
+    bool operator>(const HeapItem& o) const { return t > o.t || (t == o.t && seq > o.seq); }
+};
+struct StableQueue {                 // smallest T first, equal T in insertion order
+    std::priority_queue<HeapItem, std::vector<HeapItem>, std::greater<HeapItem>> q;
+    unsigned seq = 0;
+    void push(int i, int j, float t) { q.push({t, seq++, i, j}); }
+    bool pop(int& i, int& j) {
+        if (q.empty()) return false;
+        i = q.top().i; j = q.top().j; q.pop();
+        return true;
+    }
+};
 
-inline float eikonal(const std::vector<float>& T, const std::vector<unsigned char>& f, int rows, int cols, int i1, int j1,
-                     int i2, int j2) {
-    // solve |grad T| = 1 from the two neighbours (i1,j1), (i2,j2) (Telea 2004, fig. 4)
-    float sol = 1e6f;
-    const bool in1 = i1 >= 0 && i1 < rows && j1 >= 0 && j1 < cols, in2 = i2 >= 0 && i2 < rows && j2 >= 0 && j2 < cols;
-    const bool k1 = in1 && f[i1 * cols + j1] == KNOWN, k2 = in2 && f[i2 * cols + j2] == KNOWN;
-    const float t1 = in1 ? T[i1 * cols + j1] : 1e6f, t2 = in2 ? T[i2 * cols + j2] : 1e6f;
+struct Frame {                        // (rows + 2) x (cols + 2) planes
+    int er, ec;
+    std::vector<unsigned char> f;
+    std::vector<float> t;
+    unsigned char& F(int i, int j) { return f[(size_t)i * ec + j]; }
+    float& T(int i, int j) { return t[(size_t)i * ec + j]; }
+};
+
+// arrival time at a pixel from two of its neighbours (upwind solution of |grad T| = 1)
+inline float eikonal(Frame& m, std::vector<unsigned char>& flags, int i1, int j1, int i2, int j2) {
+    const double a11 = m.T(i1, j1), a22 = m.T(i2, j2), m12 = std::min(a11, a22);
+    const bool k1 = flags[(size_t)i1 * m.ec + j1] != INSIDE, k2 = flags[(size_t)i2 * m.ec + j2] != INSIDE;
+    double sol;
     if (k1) {
-        if (k2) {
-            const float r = std::sqrt(std::max(0.f, 2.f - (t1 - t2) * (t1 - t2)));
-            float s = (t1 + t2 - r) * 0.5f;
-            if (s >= t1 && s >= t2) sol = s;
-            else { s += r; if (s >= t1 && s >= t2) sol = s; }
-        } else {
-            sol = 1.f + t1;
-        }
-    } else if (k2) {
-        sol = 1.f + t2;
+        if (k2) sol = std::fabs(a11 - a22) >= 1.0 ? 1 + m12 : (a11 + a22 + std::sqrt(2 - (a11 - a22) * (a11 - a22))) * 0.5;
+        else sol = 1 + a11;
+    } else {
+        sol = k2 ? 1 + a22 : 1 + m12;
     }
-    return sol;
+    return (float)sol;
 }
 
-void fmm_distance(std::vector<float>& T, std::vector<unsigned char>& f, int rows, int cols, float limit) {
-    // fast marching of T over the INSIDE pixels of f starting from its BAND (no inpainting): used for the distance
-    // field OUTSIDE the hole, which gives grad T a meaning on the known side of the boundary
-    MinHeap heap;
-    for (int i = 0; i < rows * cols; i++) if (f[i] == BAND) heap.push({T[i], i});
-    const int di[4] = {-1, 0, 1, 0}, dj[4] = {0, -1, 0, 1};
-    while (!heap.empty()) {
-        HeapItem it = heap.top(); heap.pop();
-        if (f[it.idx] == KNOWN) continue;
-        f[it.idx] = KNOWN;
-        if (it.t > limit) continue;
-        const int i = it.idx / cols, j = it.idx % cols;
-        for (int q = 0; q < 4; q++) {
-            const int a = i + di[q], b = j + dj[q];
-            if (a < 0 || a >= rows || b < 0 || b >= cols || f[a * cols + b] != INSIDE) continue;
-            const float t = std::min(std::min(eikonal(T, f, rows, cols, a - 1, b, a, b - 1), eikonal(T, f, rows, cols, a + 1, b, a, b - 1)),
-                                     std::min(eikonal(T, f, rows, cols, a - 1, b, a, b + 1), eikonal(T, f, rows, cols, a + 1, b, a, b + 1)));
-            T[a * cols + b] = t;
-            f[a * cols + b] = BAND;
-            heap.push({t, a * cols + b});
-        }
-    }
+inline float eikonal4(Frame& m, std::vector<unsigned char>& flags, int i, int j) {
+    return std::min(std::min(eikonal(m, flags, i - 1, j, i, j - 1), eikonal(m, flags, i + 1, j, i, j - 1)),
+                    std::min(eikonal(m, flags, i - 1, j, i, j + 1), eikonal(m, flags, i + 1, j, i, j + 1)));
 }
 
-void inpaint_telea(std::vector<float>& img, const std::vector<unsigned char>& hole, int rows, int cols, int radius) {
-    const int n = rows * cols;
-    std::vector<unsigned char> f(n);
-    std::vector<float> T(n, 0.f);
-    const int di[4] = {-1, 0, 1, 0}, dj[4] = {0, -1, 0, 1};
+void inpaint_telea(std::vector<float>& img, const std::vector<unsigned char>& hole, int rows, int cols, int range) {
     bool any = false;
-    for (int i = 0; i < n; i++) { f[i] = hole[i] ? INSIDE : KNOWN; any |= hole[i] != 0; }
+    for (unsigned char h : hole) any |= h != 0;
     if (!any) return;
-    // distance field on the known side (negative), within 2*radius of the hole
-    {
-        std::vector<unsigned char> fo(n);
-        std::vector<float> To(n, 0.f);
-        for (int i = 0; i < n; i++) { fo[i] = hole[i] ? KNOWN : INSIDE; To[i] = hole[i] ? 0.f : 1e6f; }
-        for (int i = 0; i < rows; i++)
-            for (int j = 0; j < cols; j++) {
-                if (!hole[i * cols + j]) continue;
-                for (int q = 0; q < 4; q++) {
-                    const int a = i + di[q], b = j + dj[q];
-                    if (a >= 0 && a < rows && b >= 0 && b < cols && !hole[a * cols + b]) { fo[i * cols + j] = BAND; break; }
-                }
-            }
-        fmm_distance(To, fo, rows, cols, 2.f * radius);
-        for (int i = 0; i < n; i++) if (!hole[i]) T[i] = To[i] < 1e5f ? -To[i] : -2.f * radius;
-    }
-    MinHeap heap;
+    Frame m;
+    m.er = rows + 2; m.ec = cols + 2;
+    const int er = m.er, ec = m.ec;
+    m.f.assign((size_t)er * ec, KNOWN);
+    m.t.assign((size_t)er * ec, 1.0e6f);
+    std::vector<unsigned char> mask((size_t)er * ec, 0), band((size_t)er * ec, 0), ring((size_t)er * ec, 0);
+    auto at = [&](std::vector<unsigned char>& v, int i, int j) -> unsigned char& { return v[(size_t)i * ec + j]; };
     for (int i = 0; i < rows; i++)
-        for (int j = 0; j < cols; j++) {
-            const int id = i * cols + j;
-            if (f[id] == INSIDE) { T[id] = 1e6f; continue; }
+        for (int j = 0; j < cols; j++)
+            if (hole[(size_t)i * cols + j]) at(mask, i + 1, j + 1) = INSIDE;
+    // narrow band: known pixels 4-adjacent to the hole
+    for (int i = 1; i < er - 1; i++)
+        for (int j = 1; j < ec - 1; j++)
+            if (!at(mask, i, j) && (at(mask, i - 1, j) || at(mask, i + 1, j) || at(mask, i, j - 1) || at(mask, i, j + 1))) at(band, i, j) = 1;
+    // ring: known pixels within Chebyshev distance `range` of the hole, band excluded (separable square dilation)
+    {
+        std::vector<unsigned char> tmp((size_t)er * ec, 0);
+        for (int i = 0; i < er; i++)
+            for (int j = 0; j < ec; j++) {
+                unsigned char v = 0;
+                for (int l = std::max(0, j - range); l <= std::min(ec - 1, j + range) && !v; l++) v = at(mask, i, l);
+                at(tmp, i, j) = v;
+            }
+        for (int i = 1; i < er - 1; i++)
+            for (int j = 1; j < ec - 1; j++) {
+                unsigned char v = 0;
+                for (int k = std::max(0, i - range); k <= std::min(er - 1, i + range) && !v; k++) v = at(tmp, k, j);
+                if (v && !at(mask, i, j) && !at(band, i, j)) at(ring, i, j) = INSIDE;
+            }
+    }
+    StableQueue heap, outer;
+    for (int i = 0; i < er; i++)
+        for (int j = 0; j < ec; j++) {
+            if (at(band, i, j)) { heap.push(i, j, 0.f); outer.push(i, j, 0.f); m.F(i, j) = BAND; m.T(i, j) = 0.f; }
+            if (at(mask, i, j)) m.F(i, j) = INSIDE;
+        }
+    // T on the known side: march over the ring, then negate
+    {
+        int ii, jj;
+        while (outer.pop(ii, jj)) {
+            at(ring, ii, jj) = CHANGE;
+            const int ni[4] = {ii - 1, ii, ii + 1, ii}, nj[4] = {jj, jj - 1, jj, jj + 1};
             for (int q = 0; q < 4; q++) {
-                const int a = i + di[q], b = j + dj[q];
-                if (a >= 0 && a < rows && b >= 0 && b < cols && f[a * cols + b] == INSIDE) { f[id] = BAND; T[id] = 0.f; heap.push({0.f, id}); break; }
+                const int i = ni[q], j = nj[q];
+                if (i <= 0 || j <= 0 || i >= er - 1 || j >= ec - 1) continue;
+                if (at(ring, i, j) != INSIDE) continue;
+                const float dist = eikonal4(m, ring, i, j);
+                m.T(i, j) = dist;
+                at(ring, i, j) = BAND;
+                outer.push(i, j, dist);
             }
         }
-    while (!heap.empty()) {
-        HeapItem it = heap.top(); heap.pop();
-        if (f[it.idx] == KNOWN) continue;
-        f[it.idx] = KNOWN;
-        const int i = it.idx / cols, j = it.idx % cols;
+        for (size_t p = 0; p < ring.size(); p++)
+            if (ring[p] == CHANGE) m.t[p] = -m.t[p];
+    }
+    // inwards: T and the value of every hole pixel
+    auto I = [&](int k, int l) -> float { return img[(size_t)k * cols + l]; };
+    int ii, jj;
+    while (heap.pop(ii, jj)) {
+        m.F(ii, jj) = KNOWN;
+        const int ni[4] = {ii - 1, ii, ii + 1, ii}, nj[4] = {jj, jj - 1, jj, jj + 1};
         for (int q = 0; q < 4; q++) {
-            const int a = i + di[q], b = j + dj[q];
-            if (a < 0 || a >= rows || b < 0 || b >= cols || f[a * cols + b] != INSIDE) continue;
-            const float t = std::min(std::min(eikonal(T, f, rows, cols, a - 1, b, a, b - 1), eikonal(T, f, rows, cols, a + 1, b, a, b - 1)),
-                                     std::min(eikonal(T, f, rows, cols, a - 1, b, a, b + 1), eikonal(T, f, rows, cols, a + 1, b, a, b + 1)));
-            T[a * cols + b] = t;
-            // weighted average of the known pixels within `radius` (Telea 2004, eq. 2-3) with the weights and the
-            // normalised first-order term as OpenCV's implementation parametrises them (one-sided differences
-            // next to unknown pixels, direction term r.gradT not normalised, distance term 1/|r|^3)
-            auto fl = [&](int k, int l) -> unsigned char { return (k < 0 || k >= rows || l < 0 || l >= cols) ? (unsigned char)INSIDE : f[k * cols + l]; };
-            auto grad = [&](const std::vector<float>& A, int k, int l, int dk, int dl, float both) -> float {
-                const bool nx = fl(k + dk, l + dl) != INSIDE, pv = fl(k - dk, l - dl) != INSIDE;
-                if (nx) return pv ? (A[(k + dk) * cols + l + dl] - A[(k - dk) * cols + l - dl]) * both
-                                  : A[(k + dk) * cols + l + dl] - A[k * cols + l];
-                return pv ? A[k * cols + l] - A[(k - dk) * cols + l - dl] : 0.f;
-            };
-            const float gx = grad(T, a, b, 0, 1, 0.5f), gy = grad(T, a, b, 1, 0, 0.5f);
-            double acc = 0.0, wsum = 0.0, Jx = 0.0, Jy = 0.0;
-            for (int k = a - radius; k <= a + radius; k++) {
-                if (k < 0 || k >= rows) continue;
-                for (int l = b - radius; l <= b + radius; l++) {
-                    if (l < 0 || l >= cols || f[k * cols + l] == INSIDE) continue;
-                    const float ry = (float)(a - k), rx = (float)(b - l), d2 = rx * rx + ry * ry;
-                    if (d2 > (float)(radius * radius) || d2 == 0.f) continue;
-                    float dir = rx * gx + ry * gy;
-                    if (std::fabs(dir) <= 0.01f) dir = 1e-6f;
-                    const float dst = 1.f / (d2 * std::sqrt(d2));
-                    const float lev = 1.f / (1.f + std::fabs(T[k * cols + l] - t));
-                    const double wgt = std::fabs(dir * dst * lev);
-                    acc += wgt * img[k * cols + l];
-                    Jx -= wgt * grad(img, k, l, 0, 1, 2.0f) * rx;
-                    Jy -= wgt * grad(img, k, l, 1, 0, 2.0f) * ry;
-                    wsum += wgt;
+            const int i = ni[q], j = nj[q];
+            if (i <= 0 || j <= 0 || i > er - 1 || j > ec - 1) continue;
+            if (m.F(i, j) != INSIDE) continue;
+            const float dist = eikonal4(m, m.f, i, j);
+            m.T(i, j) = dist;
+            float gTx, gTy;
+            if (m.F(i, j + 1) != INSIDE) gTx = m.F(i, j - 1) != INSIDE ? (m.T(i, j + 1) - m.T(i, j - 1)) * 0.5f : m.T(i, j + 1) - m.T(i, j);
+            else gTx = m.F(i, j - 1) != INSIDE ? m.T(i, j) - m.T(i, j - 1) : 0.f;
+            if (m.F(i + 1, j) != INSIDE) gTy = m.F(i - 1, j) != INSIDE ? (m.T(i + 1, j) - m.T(i - 1, j)) * 0.5f : m.T(i + 1, j) - m.T(i, j);
+            else gTy = m.F(i - 1, j) != INSIDE ? m.T(i, j) - m.T(i - 1, j) : 0.f;
+            float Ia = 0.f, Jx = 0.f, Jy = 0.f, s = 1.0e-20f;
+            for (int k = i - range; k <= i + range; k++) {
+                if (k <= 0 || k >= er - 1) continue;
+                const int km = k - 1 + (k == 1), kp = k - 1 - (k == er - 2);          // clamped rows of the one-sided differences
+                for (int l = j - range; l <= j + range; l++) {
+                    if (l <= 0 || l >= ec - 1) continue;
+                    if (m.F(k, l) == INSIDE || (l - j) * (l - j) + (k - i) * (k - i) > range * range) continue;
+                    const int lm = l - 1 + (l == 1), lp = l - 1 - (l == ec - 2);
+                    const float ry = (float)(i - k), rx = (float)(j - l);
+                    const float len2 = rx * rx + ry * ry;
+                    const float dst = (float)(1.0 / ((double)len2 * std::sqrt((double)len2)));
+                    const float lev = (float)(1.0 / (double)(1.f + std::fabs(m.T(k, l) - m.T(i, j))));
+                    float dir = rx * gTx + ry * gTy;
+                    if (std::fabs((double)dir) <= 0.01) dir = 0.000001f;
+                    const float w = std::fabs(dst * lev * dir);
+                    float gIx, gIy;
+                    if (m.F(k, l + 1) != INSIDE) gIx = m.F(k, l - 1) != INSIDE ? (I(km, lp + 1) - I(km, lm - 1)) * 2.0f : I(km, lp + 1) - I(km, lm);
+                    else gIx = m.F(k, l - 1) != INSIDE ? I(km, lp) - I(km, lm - 1) : 0.f;
+                    if (m.F(k + 1, l) != INSIDE) gIy = m.F(k - 1, l) != INSIDE ? (I(kp + 1, lm) - I(km - 1, lm)) * 2.0f : I(kp + 1, lm) - I(km, lm);
+                    else gIy = m.F(k - 1, l) != INSIDE ? I(kp, lm) - I(km - 1, lm) : 0.f;
+                    Ia += w * I(k - 1, l - 1);
+                    Jx -= w * (gIx * rx);
+                    Jy -= w * (gIy * ry);
+                    s += w;
                 }
             }
-            if (wsum > 0.0) img[a * cols + b] = (float)(acc / wsum + (Jx + Jy) / (std::sqrt(Jx * Jx + Jy * Jy) + 1.0e-20));
-            f[a * cols + b] = BAND;
-            heap.push({t, a * cols + b});
+            img[(size_t)(i - 1) * cols + (j - 1)] = Ia / s + (Jx + Jy) / (std::sqrt(Jx * Jx + Jy * Jy) + 1.0e-20f);
+            m.F(i, j) = BAND;
+            heap.push(i, j, dist);
         }
     }
 }

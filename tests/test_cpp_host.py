@@ -76,17 +76,20 @@ def test_image_loader_and_init_match_python_mirror(cli, tmp_path):
     assert np.array_equal(snap["K"], dh.K)
     assert np.array_equal(snap["I"], I)                       # PNG decode + /255 + channel order: bit-exact
     assert snap["z0s"].shape == z0s.shape and snap["z"].shape == z.shape
-    # no zero depth samples -> no inpainting: bilateral + bicubic only, cv2 uses a LUT for exp()
-    assert np.abs(snap["z0s"] - z0s).max() <= 2e-3 * np.abs(z0s).max()
-    assert np.abs(snap["z"] - z).max() <= 2e-3 * np.abs(z).max()
+    # no zero depth samples -> no inpainting: bilateral + bicubic only
+    assert np.abs(snap["z0s"] - z0s).max() <= 2e-6 * np.abs(z0s).max()
+    assert np.abs(snap["z"] - z).max() <= 2e-6 * np.abs(z).max()
 
 
-def test_init_with_depth_dropout_stays_close_to_cv2(cli, tmp_path):
-    folder = write_image_folder(str(tmp_path / "scene"), dropout=0.02, seed=3)
-    snap = run_init(cli, "images", folder, str(tmp_path / "init.snap"))
-    dh, I, z, z0s, mflat = python_init(folder)
-    rel = np.abs(snap["z"] - z) / np.abs(z)
-    assert np.median(rel) < 2e-3 and rel.max() < 0.1          # Telea inpainting: not bit-identical to OpenCV
+def test_init_with_depth_dropout_matches_cv2(cli, tmp_path):
+    """Telea inpainting in OpenCV's parametrisation (Preprocess.cpp) + bilateral + bicubic against python cv2:
+    agreement to a few ulp even with 2 % / 10 % of the depth samples missing (holes on the image border included)."""
+    for dropout, seed in ((0.02, 3), (0.10, 4)):
+        folder = write_image_folder(str(tmp_path / f"scene{seed}"), dropout=dropout, seed=seed)
+        snap = run_init(cli, "images", folder, str(tmp_path / "init.snap"))
+        dh, I, z, z0s, mflat = python_init(folder)
+        assert np.abs(snap["z0s"] - z0s).max() <= 2e-6 * np.abs(z0s).max()
+        assert np.abs(snap["z"] - z).max() <= 2e-6 * np.abs(z).max()
 
 
 def test_mat_loader(cli, tmp_path):
@@ -114,7 +117,7 @@ def test_mitten_loaders_bit_exact(cli, tmp_path):
     assert np.array_equal(snap["mask"], ref["mask"].ravel(order="F"))
     assert np.array_equal(snap["I"], (ref["I8"].astype(np.float32) / np.float32(255)))
     d = snap["z"] - ref["z"]
-    assert np.sqrt((d ** 2).mean()) < 0.2 and np.abs(d).max() < 5.0        # z in [535, 570]; OpenCV-free inpainting
+    assert np.sqrt((d ** 2).mean()) < 5e-4 and np.abs(d).max() < 2e-2       # z in [535, 570]; measured: rms 9e-5, max 3e-3
 
 
 @pytest.mark.gpu
