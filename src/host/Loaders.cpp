@@ -73,13 +73,15 @@ std::vector<std::string> list_sorted(const std::string& dir) {
 // ---- PNG: non-interlaced, colour types 0/2/4/6, 8 or 16 bit (what the reference's datasets contain) ----
 static inline uint32_t be32(const unsigned char* p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
 
+// 8/16-bit gray, gray+alpha, RGB, RGBA; 1/2/4/8-bit gray and palette; Adam7 interlacing.  Like cv::imread: alpha is
+// dropped, palettes are expanded to RGB, gray samples below 8 bits are scaled to the full 8-bit range.
 PngImage read_png(const std::string& path) {
     std::vector<unsigned char> f = read_file(path);
     static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
     if (f.size() < 8 || memcmp(f.data(), sig, 8) != 0) throw std::runtime_error(path + ": not a PNG file");
     PngImage img;
     int ctype = -1, interlace = 0;
-    std::vector<unsigned char> idat;
+    std::vector<unsigned char> idat, plte;
     size_t pos = 8;
     while (pos + 8 <= f.size()) {
         uint32_t len = be32(&f[pos]);
@@ -88,6 +90,8 @@ PngImage read_png(const std::string& path) {
         if (pos + 12 + len > f.size()) throw std::runtime_error(path + ": truncated PNG chunk");
         if (type == "IHDR") {
             img.w = (int)be32(data); img.h = (int)be32(data + 4); img.bits = data[8]; ctype = data[9]; interlace = data[12];
+        } else if (type == "PLTE") {
+            plte.assign(data, data + len);
         } else if (type == "IDAT") {
             idat.insert(idat.end(), data, data + len);
         } else if (type == "IEND") {
@@ -95,39 +99,79 @@ PngImage read_png(const std::string& path) {
         }
         pos += 12 + len;
     }
-    if (interlace || (img.bits != 8 && img.bits != 16) || !(ctype == 0 || ctype == 2 || ctype == 4 || ctype == 6))
-        throw std::runtime_error(path + ": unsupported PNG flavour");
-    const int src_ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 4 ? 2 : 4;
-    img.channels = (ctype == 0 || ctype == 4) ? 1 : 3;            // alpha dropped
-    const int bpp = src_ch * img.bits / 8;
-    const size_t stride = (size_t)img.w * bpp;
-    std::vector<unsigned char> raw = inflate_all(idat.data(), idat.size(), (stride + 1) * img.h);
-    if (raw.size() < (stride + 1) * img.h) throw std::runtime_error(path + ": short PNG data");
-    std::vector<unsigned char> prev(stride, 0), cur(stride);
-    img.px.resize((size_t)img.w * img.h * img.channels);
-    for (int y = 0; y < img.h; y++) {
-        const unsigned char* line = &raw[(stride + 1) * y];
-        const int ft = line[0];
-        for (size_t i = 0; i < stride; i++) {
-            const int a = i >= (size_t)bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= (size_t)bpp ? prev[i - bpp] : 0;
-            int pr = 0;
-            switch (ft) {
-                case 0: pr = 0; break;
-                case 1: pr = a; break;
-                case 2: pr = b; break;
-                case 3: pr = (a + b) / 2; break;
-                case 4: { int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
-                          pr = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
-                default: throw std::runtime_error(path + ": bad PNG filter");
+    const int bits = img.bits;
+    const bool low = bits == 1 || bits == 2 || bits == 4;
+    const bool ok = (ctype == 0 && (low || bits == 8 || bits == 16)) || (ctype == 3 && (low || bits == 8) && !plte.empty()) ||
+                    ((ctype == 2 || ctype == 4 || ctype == 6) && (bits == 8 || bits == 16));
+    if (!ok || interlace > 1) throw std::runtime_error(path + ": unsupported PNG flavour");
+    const int src_ch = (ctype == 0 || ctype == 3) ? 1 : ctype == 2 ? 3 : ctype == 4 ? 2 : 4;
+    img.channels = (ctype == 0 || ctype == 4) ? 1 : 3;            // alpha dropped, palette expanded
+    if (ctype == 3) img.bits = 8;
+    else if (low) img.bits = 8;
+    const int bpp = std::max(1, src_ch * bits / 8);              // filter distance in bytes
+    auto line_bytes = [&](int wpx) { return ((size_t)wpx * src_ch * bits + 7) / 8; };
+
+    // pass geometry: one pass for a plain image, seven for Adam7
+    struct Pass { int x0, y0, dx, dy; };
+    static const Pass adam7[7] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+    static const Pass whole[1] = {{0, 0, 1, 1}};
+    const Pass* passes = interlace ? adam7 : whole;
+    const int npass = interlace ? 7 : 1;
+    size_t need = 0;
+    for (int p = 0; p < npass; p++) {
+        const int pw = (img.w - passes[p].x0 + passes[p].dx - 1) / passes[p].dx, ph = (img.h - passes[p].y0 + passes[p].dy - 1) / passes[p].dy;
+        if (pw > 0 && ph > 0) need += (line_bytes(pw) + 1) * ph;
+    }
+    std::vector<unsigned char> raw = inflate_all(idat.data(), idat.size(), need);
+    if (raw.size() < need) throw std::runtime_error(path + ": short PNG data");
+    img.px.assign((size_t)img.w * img.h * img.channels, 0);
+    size_t off = 0;
+    for (int p = 0; p < npass; p++) {
+        const Pass& ps = passes[p];
+        const int pw = (img.w - ps.x0 + ps.dx - 1) / ps.dx, ph = (img.h - ps.y0 + ps.dy - 1) / ps.dy;
+        if (pw <= 0 || ph <= 0) continue;
+        const size_t stride = line_bytes(pw);
+        std::vector<unsigned char> prev(stride, 0), cur(stride);
+        for (int y = 0; y < ph; y++) {
+            const unsigned char* line = &raw[off];
+            off += stride + 1;
+            const int ft = line[0];
+            for (size_t i = 0; i < stride; i++) {
+                const int a = i >= (size_t)bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= (size_t)bpp ? prev[i - bpp] : 0;
+                int pr = 0;
+                switch (ft) {
+                    case 0: pr = 0; break;
+                    case 1: pr = a; break;
+                    case 2: pr = b; break;
+                    case 3: pr = (a + b) / 2; break;
+                    case 4: { int q = a + b - c, pa = std::abs(q - a), pb = std::abs(q - b), pc = std::abs(q - c);
+                              pr = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
+                    default: throw std::runtime_error(path + ": bad PNG filter");
+                }
+                cur[i] = (unsigned char)(line[1 + i] + pr);
             }
-            cur[i] = (unsigned char)(line[1 + i] + pr);
+            const int oy = ps.y0 + y * ps.dy;
+            for (int x = 0; x < pw; x++) {
+                const int ox = ps.x0 + x * ps.dx;
+                uint16_t* dst = &img.px[((size_t)oy * img.w + ox) * img.channels];
+                if (low || ctype == 3) {
+                    const size_t bit = (size_t)x * bits;
+                    const int v = bits == 8 ? cur[x] : (cur[bit / 8] >> (8 - bits - (int)(bit % 8))) & ((1 << bits) - 1);
+                    if (ctype == 3) {
+                        if ((size_t)v * 3 + 2 >= plte.size()) throw std::runtime_error(path + ": palette index out of range");
+                        for (int ch = 0; ch < 3; ch++) dst[ch] = plte[(size_t)v * 3 + ch];
+                    } else {
+                        dst[0] = (uint16_t)(v * 255 / ((1 << bits) - 1));
+                    }
+                } else {
+                    for (int ch = 0; ch < img.channels; ch++) {
+                        const unsigned char* q = &cur[(size_t)x * bpp + (size_t)ch * bits / 8];
+                        dst[ch] = bits == 8 ? q[0] : (uint16_t)(q[0] << 8 | q[1]);
+                    }
+                }
+            }
+            prev.swap(cur);
         }
-        for (int x = 0; x < img.w; x++)
-            for (int ch = 0; ch < img.channels; ch++) {
-                const unsigned char* p = &cur[(size_t)x * bpp + (size_t)ch * img.bits / 8];
-                img.px[((size_t)y * img.w + x) * img.channels + ch] = img.bits == 8 ? p[0] : (uint16_t)(p[0] << 8 | p[1]);
-            }
-        prev.swap(cur);
     }
     return img;
 }
@@ -138,11 +182,23 @@ void ImageDataHandler::loadDataFromImages(const char* dataFolder) {
     const std::string root(dataFolder);
     std::vector<std::string> files = list_sorted(root + "/RGB");
     if (files.empty()) throw std::runtime_error("no images in " + root + "/RGB");
-    PngImage first = read_png(files[0]);
+    auto read_color = [](const std::string& file) {          // cv::imread(file): always 3 channels, 8 bit
+        PngImage im = read_png(file);
+        if (im.bits == 16) { for (auto& v : im.px) v >>= 8; im.bits = 8; }
+        if (im.channels == 1) {
+            PngImage c = im;
+            c.channels = 3;
+            c.px.resize((size_t)im.w * im.h * 3);
+            for (size_t p = 0; p < (size_t)im.w * im.h; p++) c.px[3 * p] = c.px[3 * p + 1] = c.px[3 * p + 2] = im.px[p];
+            return c;
+        }
+        return im;
+    };
+    PngImage first = read_color(files[0]);
     I_n = (int)files.size(); I_w = first.w; I_h = first.h; I_c = first.channels;
     I = new float[(size_t)I_h * I_w * I_c * I_n];
     for (int n = 0; n < I_n; n++) {
-        PngImage im = n == 0 ? first : read_png(files[n]);
+        PngImage im = n == 0 ? first : read_color(files[n]);
         if (im.w != I_w || im.h != I_h || im.channels != I_c) throw std::runtime_error(files[n] + ": size mismatch");
         float* dst = I + (size_t)n * I_w * I_h * I_c;
         // cv::imread gives BGR and the reference stores channel (channels-1-c) (Utilities.cpp:343): plane 0 = R
@@ -169,8 +225,12 @@ void ImageDataHandler::loadDataFromImages(const char* dataFolder) {
     if (m.w != I_w || m.h != I_h) throw std::runtime_error("mask.png: size mismatch");
     mask = new float[(size_t)I_h * I_w];
     for (int i = 0; i < I_h; i++)
-        for (int j = 0; j < I_w; j++)                          // grayscale: first channel of a gray file
-            mask[(size_t)i + (size_t)j * I_h] = m.px[((size_t)i * I_w + j) * m.channels] / 255.f;
+        for (int j = 0; j < I_w; j++) {                        // IMREAD_GRAYSCALE: a colour mask is converted (BT.601 weights)
+            const uint16_t* px = &m.px[((size_t)i * I_w + j) * m.channels];
+            int g = m.channels == 1 ? px[0] : (px[0] * 4899 + px[1] * 9617 + px[2] * 1868 + 8192) >> 14;
+            if (m.bits == 16) g >>= 8;
+            mask[(size_t)i + (size_t)j * I_h] = g / 255.f;
+        }
     files = list_sorted(root + "/Depth");
     z0_n = (int)files.size();
     z0_h = (int)(I_h / sf); z0_w = (int)(I_w / sf);

@@ -184,3 +184,54 @@ def test_images_to_mat_round_trip(tmp_path):
     assert (a.I_h, a.I_w, a.I_c, a.I_n, int(a.sf), a.z0.shape) == (b.I_h, b.I_w, b.I_c, b.I_n, int(b.sf), b.z0.shape)
     assert np.array_equal(a.I, b.I) and np.array_equal(a.K, b.K) and np.array_equal(a.z0, b.z0)
     assert np.array_equal(a.mask != 0, b.mask != 0)
+
+
+def _write_interlaced_png(path, img):
+    """8-bit gray or RGB Adam7-interlaced PNG (neither cv2 nor Pillow writes one)."""
+    import struct
+    import zlib
+    img = np.ascontiguousarray(img)
+    h, w = img.shape[:2]
+    c = 1 if img.ndim == 2 else 3
+    raw = b""
+    for x0, y0, dx, dy in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+        sub = img[y0::dy, x0::dx]
+        if sub.size:
+            raw += b"".join(b"\0" + sub[r].tobytes() for r in range(sub.shape[0]))
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2 if c == 3 else 0, 0, 0, 1))
+                + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b""))
+
+
+def test_png_flavours_load_like_cv_imread(cli, tmp_path):
+    """N3: the zlib PNG reader against cv::imread semantics (python cv2 on the same files): palette, RGBA, gray and
+    Adam7-interlaced images in RGB/, 1-bit / palette / colour masks."""
+    import cv2
+    from PIL import Image
+    folder = write_image_folder(str(tmp_path / "scene"), n=4, seed=5)
+    rgb = sorted(os.listdir(os.path.join(folder, "RGB")))
+    imgs = [cv2.imread(os.path.join(folder, "RGB", f))[:, :, ::-1] for f in rgb]
+    Image.fromarray(imgs[0]).quantize(32).save(os.path.join(folder, "RGB", rgb[0]))                     # palette, 8 bit
+    Image.fromarray(np.dstack([imgs[1], np.full(imgs[1].shape[:2], 77, np.uint8)])).save(os.path.join(folder, "RGB", rgb[1]))   # RGBA
+    Image.fromarray(imgs[2][:, :, 1]).save(os.path.join(folder, "RGB", rgb[2]))                          # gray
+    _write_interlaced_png(os.path.join(folder, "RGB", rgb[3]), imgs[3])                                  # Adam7
+    mask = cv2.imread(os.path.join(folder, "mask.png"), cv2.IMREAD_GRAYSCALE)
+    for kind in ("bit1", "palette4", "colour", "interlaced"):
+        mp = os.path.join(folder, "mask.png")
+        if kind == "bit1":
+            Image.fromarray(mask > 0).save(mp)
+        elif kind == "palette4":
+            Image.fromarray(np.dstack([mask, mask, mask])).quantize(4).save(mp, bits=2)
+        elif kind == "colour":
+            Image.fromarray(np.dstack([mask, mask, mask])).save(mp)
+        else:
+            _write_interlaced_png(mp, mask)
+        snap = run_init(cli, "images", folder, str(tmp_path / "init.snap"))
+        dh, I, z, z0s, mflat = python_init(folder)
+        assert list(snap["dims"]) == [dh.I_h, dh.I_w, int(dh.sf)], kind
+        assert np.array_equal(snap["mask"].astype(bool), mflat), kind
+        assert np.array_equal(snap["I"], I), kind
