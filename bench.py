@@ -35,8 +35,10 @@ WORKLOADS = {
     # name: (h, w, sf, n, seed)        BASELINE.md §3
     "4k": (4096, 4096, 4, 32, 2000),         # config 4 (the metric's configuration)
     "1080p": (1080, 1920, 4, 20, 1000),      # config 3
+    "1k": (1024, 1024, 4, 32, 2000),         # the largest square both arms can run: the same-size pair of the reference ratio
     "small": (512, 512, 4, 8, 7),            # CI-sized
 }
+PARITY_SCENE = (1024, 1024, 4, 8, 77, 3)     # strip_parity: h, w, sf, n, seed, outer iterations
 METRIC = "ms per outer iteration (4096x4096 HR, sf=4, 32 images)"
 
 
@@ -169,9 +171,17 @@ def run_reference(args, rank, world):
                                  capture_output=True, text=True)
         rows = [json.loads(ln.replace(": nan", ": NaN")) for ln in res.stdout.splitlines() if ln.startswith('{"iteration"')]
         if res.returncode == 0 and len(rows) >= args.steps + args.warmup:
-            ms = float(np.mean([r["ms_total"] for r in rows[args.warmup:]]))
+            timed = [float(r["ms_total"]) for r in rows[args.warmup:]]
+            ms = float(np.mean(timed))
             scale = full_pixels / float(sh * sw)
             line.update({"value": ms * scale, "ms_per_step": ms * scale,
+                         # the reference cannot run the 4096^2 x 32 workload: `value` is a per-pixel-linear
+                         # extrapolation of the sample; `same_size` is the un-scaled measurement, to be set against the
+                         # `same_size` block of this repo's own line (bench.py --workload 1k reproduces both)
+                         "same_config": bool(scale == 1.0), "extrapolated": bool(scale != 1.0),
+                         "same_size": {"workload": f"{sh}x{sw} HR, sf={sf}, {n} images, full mask", "value": ms, "unit": "ms",
+                                       "min": float(np.min(timed)), "median": float(np.median(timed)), "max": float(np.max(timed)),
+                                       "steps": len(timed)},
                          "config": {"workload": f"{h}x{w} sf={sf} n={n}", "sample": f"{sh}x{sw}", "scaled_by": scale},
                          "cpu_baseline": {"value": ms * scale, "unit": "ms per outer iteration", "cores": 1, "kind": "reference",
                                           "sample": f"reference CUDA build (cuSPARSE/cuBLAS path on the GPU, no CPU path exists) on "
@@ -190,23 +200,20 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_batch(args, rank, world, local):
-    """BASELINE config 5: every GPU processes `--batch-scenes` independent 1080p scenes back to back, fixed
-    10 outer iterations each, the upload of scene k+1 (other context, other stream, host thread) overlapping the
-    iterations of scene k.  Metric: scenes/s for the box, uploads and the download of z included.  Separate mode: the
-    default bench line stays BASELINE's headline metric.  (Written in round 1, not yet measured on a GPU.)"""
+def batch_scenes(local, world, rank, S, albedo, iters=10):
+    """BASELINE config 5: this GPU processes S independent 1080p scenes back to back, fixed 10 outer
+    iterations each; the upload of scene k+1 (other context, other stream, a host thread -- ctypes releases the GIL
+    inside the library) overlaps the iterations of scene k.  Returns scenes/s of this process and the counters."""
     import threading
 
-    import numpy as np
     import torch
     from srmeetsps_cuda_b200 import Context
     from srmeetsps_cuda_b200.synth import synth_scene_torch
     h, w, sf, n, seed0 = WORKLOADS["1080p"]
-    S, iters = args.batch_scenes, 10
     torch.cuda.set_device(local)
     scenes = [synth_scene_torch(h, w, sf, n, seed0 + rank * S + k, device=f"cuda:{local}") for k in range(S)]   # pinned host arrays
     torch.cuda.empty_cache()
-    ctxs = [Context(scenes[0]["mask"], n, sf, scenes[0]["K"], device=local, albedo_mode=args.albedo) for _ in range(2)]
+    ctxs = [Context(scenes[0]["mask"], n, sf, scenes[0]["K"], device=local, albedo_mode=albedo) for _ in range(2)]
     zout = torch.empty(ctxs[0].npix, dtype=torch.float32, pin_memory=True).numpy()
 
     def upload(k):
@@ -218,9 +225,9 @@ def run_batch(args, rank, world, local):
         for k in range(S):
             nxt = None
             if k + 1 < S:
-                nxt = threading.Thread(target=upload, args=(k + 1,))      # ctypes releases the GIL inside the library
+                nxt = threading.Thread(target=upload, args=(k + 1,))
                 nxt.start()
-            energies.append(ctxs[k & 1].run(fixed_iters=iters)[-1])
+            energies.append(float(ctxs[k & 1].run(fixed_iters=iters)[-1]))
             ctxs[k & 1].download("z", out=zout)
             if nxt is not None:
                 nxt.join()
@@ -240,19 +247,134 @@ def run_batch(args, rank, world, local):
     launches = sum(c.timings()["launches"] for c in ctxs) // 2             # one of the two rounds
     for c in ctxs:
         c.close()
+    sc = scenes[0]
+    res = {"workload": f"BASELINE config 5: {S} scenes per GPU x {world} GPU(s), {h}x{w} HR, sf={sf}, {n} images, full mask, "
+                       f"{iters} outer iterations each, double-buffered upload",
+           "value": world * S / dt, "unit": "scenes/s", "seconds": dt, "scenes": world * S,
+           "h2d_bytes_per_scene": float(sc["I"].nbytes + sc["z"].nbytes + sc["z0s"].nbytes), "d2h_bytes_per_scene": float(zout.nbytes),
+           "gpu_launches": int(launches), "clocks": clocks, "energy_last": float(energies[-1]),
+           "energies_finite": bool(all(e == e and abs(e) < 1e30 for e in energies))}
+    del scenes
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_batch(args, rank, world, local):
+    """bench.py --batch-scenes S [--gpus N]: BASELINE config 5 as its own line (scenes/s for the box, uploads and the
+    download of z included); the default bench line stays BASELINE's headline metric."""
+    S = args.batch_scenes
+    r = batch_scenes(local, world, rank, S, args.albedo)
     if rank != 0:
         return
-    sc = scenes[0]
     print(json.dumps({
         "metric": f"scenes/s ({world * S} synthetic 1080p scenes, sf=4, 20 images, 10 outer iterations each, uploads included)",
-        "value": world * S / dt, "unit": "scenes/s", "n_gpus": world, "steps": S, "warmup": S, "ms_per_step": dt / S * 1e3,
+        "value": r["value"], "unit": "scenes/s", "n_gpus": world, "steps": S, "warmup": S, "ms_per_step": r["seconds"] / S * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE config 5: {S} scenes per GPU, {h}x{w} HR, sf={sf}, {n} images, full mask",
-                   "albedo": args.albedo, "parallelism": f"{world} GPU(s), independent scenes, double-buffered upload",
+        "config": {"workload": r["workload"], "albedo": args.albedo,
+                   "parallelism": f"{world} GPU(s), independent scenes, double-buffered upload",
                    "l2": "image stack 0.5 GB per scene: exceeds the 126 MB L2"},
-        "e2e": {"value": world * S / dt, "unit": "scenes/s",
-                "h2d_bytes_per_step": float(sc["I"].nbytes + sc["z"].nbytes + sc["z0s"].nbytes), "d2h_bytes_per_step": float(zout.nbytes)},
-        "gpu_launches": int(launches), "clocks": clocks, "energy_last": float(energies[-1])}))
+        "e2e": {"value": r["value"], "unit": "scenes/s", "h2d_bytes_per_step": r["h2d_bytes_per_scene"],
+                "d2h_bytes_per_step": r["d2h_bytes_per_scene"]},
+        "gpu_launches": r["gpu_launches"], "clocks": r["clocks"], "energy_last": r["energy_last"]}))
+
+
+# ------------------------------------------------------------------------------------------------
+def strip_parity_check(rank, world, local, albedo):
+    """N > 1, before the timed region: the strip partition against ONE GPU on the same host arrays.
+
+    A 1024x1024x8 full-mask scene (sf 4) is generated once per rank from the same counter-based noise (identical
+    arrays everywhere), rank 0 runs it in a single-GPU context, all ranks run their strips of it; after each of 3
+    outer iterations the gathered z / rho / s are compared.  Only the fp64 summation order of the dot products differs
+    between the two runs.  The bench fails when the partition changes the result beyond fp32 round-off."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from srmeetsps_cuda_b200 import Context
+    from srmeetsps_cuda_b200.dist import make_strip_context, strip_bounds
+    from srmeetsps_cuda_b200.synth import synth_scene_torch
+    h, w, sf, n, seed, iters = PARITY_SCENE
+    full = synth_scene_torch(h, w, sf, n, seed, device=f"cuda:{local}", pin=False)
+    ref = []
+    if rank == 0:
+        with Context(full["mask"], n, sf, full["K"], device=local, albedo_mode=albedo) as c1:
+            c1.upload_state(full["I"], full["z"], full["z0s"])
+            for _ in range(iters):
+                e, k = c1.outer_iteration()
+                ref.append((e, k, c1.download("z"), c1.download("rho"), c1.download("s")))
+    dist.barrier()
+    j0, j1 = strip_bounds(w, world)[rank]
+    p0, p1, q0, q1 = j0 * h, j1 * h, (j0 // sf) * (h // sf), (j1 // sf) * (h // sf)
+    ctx = make_strip_context(full["mask"], n, sf, full["K"], rank, world, local, albedo_mode=albedo)
+    assert ctx.pixel_range() == (p0, p1, q0, q1)
+    ctx.upload_state_strided(np.ascontiguousarray(full["I"]).reshape(-1)[p0:], h * w, full["z"][p0:p1], full["z0s"][q0:q1])
+    out = {"scene": f"{h}x{w} HR, sf={sf}, {n} images, full mask, {iters} outer iterations, strips vs 1 GPU from the same host arrays",
+           "z_rel_rmse": 0.0, "rho_maxabs": 0.0, "s_maxabs": 0.0, "energy_rel": 0.0, "cg_iters": [], "cg_iters_1gpu": [],
+           "bit_identical_full_mask": True, "ranks_agree": True}
+    for it in range(iters):
+        e, k = ctx.outer_iteration()
+        parts = [None] * world
+        dist.all_gather_object(parts, (ctx.download("z"), ctx.download("rho"), ctx.download("s"), e, k))
+        if rank == 0:
+            z = np.concatenate([p[0] for p in parts]); rho = np.concatenate([p[1] for p in parts], axis=1)
+            e1, k1, z1, rho1, s1 = ref[it]
+            out["ranks_agree"] &= all(p[3] == parts[0][3] and p[4] == parts[0][4] and np.array_equal(p[2], parts[0][2]) for p in parts)
+            zr = float(np.sqrt(np.mean((z.astype(np.float64) - z1) ** 2)) / np.sqrt(np.mean(z1.astype(np.float64) ** 2)))
+            out["z_rel_rmse"] = max(out["z_rel_rmse"], zr)
+            out["rho_maxabs"] = max(out["rho_maxabs"], float(np.abs(rho - rho1).max()))
+            out["s_maxabs"] = max(out["s_maxabs"], float(np.abs(parts[0][2] - s1).max()))
+            out["energy_rel"] = max(out["energy_rel"], abs(e - e1) / abs(e1))
+            out["cg_iters"].append(int(k)); out["cg_iters_1gpu"].append(int(k1))
+            out["bit_identical_full_mask"] &= bool(np.array_equal(z, z1) and np.array_equal(rho, rho1))
+    ctx.close()
+    ok = True
+    if rank == 0:
+        # north-star bound / 10: the two runs differ by the summation order of fp64 dot products only
+        ok = (out["ranks_agree"] and out["z_rel_rmse"] <= 1e-5 and out["rho_maxabs"] <= 1e-4 and out["energy_rel"] <= 1e-4
+              and all(abs(a - b) <= 1 for a, b in zip(out["cg_iters"], out["cg_iters_1gpu"])))
+        out["ok"] = bool(ok)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    del full
+    torch.cuda.empty_cache()
+    if int(flag.item()) != 1:
+        if rank == 0:
+            sys.stderr.write("strip_parity FAILED: " + json.dumps(out) + "\n")
+        dist.barrier()
+        sys.exit(3)
+    return out
+
+
+def time_workload(name, local, albedo, steps, warmup):
+    """One single-GPU workload timed the way the headline is (device-resident value, e2e from pinned host): the
+    same-size leg of the reference ratio and the config-3 line."""
+    import numpy as np
+    import torch
+    from srmeetsps_cuda_b200 import Context
+    from srmeetsps_cuda_b200.synth import synth_scene_torch
+    h, w, sf, n, seed = WORKLOADS[name]
+    sc = synth_scene_torch(h, w, sf, n, seed, device=f"cuda:{local}")
+    with Context(sc["mask"], n, sf, sc["K"], device=local, albedo_mode=albedo) as ctx:
+        ctx.upload_state(sc["I"], sc["z"], sc["z0s"])
+        for _ in range(warmup):
+            ctx.outer_iteration()
+        per, cg = [], []
+        for _ in range(steps):
+            _, k = ctx.outer_iteration()
+            t = ctx.timings()
+            per.append(t["ms_total"]); cg.append(t["ms_depth_cg"])
+        out = {k: torch.empty(s_, dtype=torch.float32, pin_memory=True).numpy() for k, s_ in
+               (("z", (ctx.npix,)), ("rho", (3, ctx.npix)), ("N", (4, ctx.npix)), ("s", (n, 3, 4)))}
+        ctx.timer_start()
+        ctx.upload_state(sc["I"], sc["z"], sc["z0s"])
+        ctx.run(fixed_iters=steps)
+        for k in out:
+            ctx.download(k, out=out[k])
+        e2e = ctx.timer_stop() / steps
+    del sc
+    torch.cuda.empty_cache()
+    return {"workload": f"{h}x{w} HR, sf={sf}, {n} images, full mask", "value": float(np.mean(per)), "unit": "ms",
+            "min": float(np.min(per)), "median": float(np.median(per)), "e2e": float(e2e), "steps": steps, "warmup": warmup,
+            "ms_depth_cg": float(np.mean(cg)), "cg_iters": int(k)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -266,6 +388,7 @@ def run_ours(args, rank, world, local):
     h, w, sf, n, seed = WORKLOADS[args.workload]
     torch.cuda.set_device(local)
     strips = world > 1 and args.parallelism == "strips"
+    parity = strip_parity_check(rank, world, local, args.albedo) if strips else None
     if strips:
         # ONE scene, strip-partitioned along the image columns (BASELINE config 4 at 2/4/8 GPUs): ghost lines and
         # CG scalars travel inside the library's kernels over NVLink peer memory (csrc/srps_comm.cuh)
@@ -319,13 +442,16 @@ def run_ours(args, rank, world, local):
     e2e_ms_total = ctx.timer_stop()
     e2e_ms = max_over_ranks(e2e_ms_total / args.steps, world)
     h2d = (sc["I"].nbytes + sc["z"].nbytes + sc["z0s"].nbytes) / args.steps
+    stack_gb = sc["I"].nbytes / 1e9
     d2h = sum(v.nbytes for v in out.values()) / args.steps + 16
 
     # ---- roofline of the dominant kernel of the CG driver in use, timed alone
     prof = ctx.profile_kernels(reps=30)
     peak, peak_src = measured_peaks()
-    fused = prof["cg_driver"] == "fused"
+    fused = prof["cg_driver"] in ("fused", "persistent_fused")
     if fused:      # one kernel per pass: reads r, y, p, z, w0..2 ; writes r, p, y, z  
+        # (persistent_fused runs the same passes inside one cooperative launch: the pass is timed alone in its
+        #  one-kernel-per-pass form, the in-loop figure is cg_loop_GBps_actual below)
         kernel = "cg_fused_kernel<sf> (CG pass: r -= alpha y; z += alpha p; p <- r + beta p; y <- (KtK + GtMG) p; r.r, p.y, r.y, y.y)"
         bytes_px, ms_kernel, tkey = 44.0, prof["cg_fused"], "cg_fused"
     else:          # operator kernel of the two-kernel form: reads r, p, w0..2 ; writes p, y
@@ -333,16 +459,22 @@ def run_ours(args, rank, world, local):
         bytes_px, ms_kernel, tkey = 28.0, prof["cg_stencil"], "cg_operator"
     alg_bytes = bytes_px * npix
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the committed ncu --set full capture
+    # of this workload on ONE GPU (profiles/traffic.json, written by profiles/summarize.py).  A strip of the scene is
+    # another launch geometry: no capture, no number (ncu cannot wrap a multi-rank run).
     traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get(args.workload, {}).get(tkey)
-    except Exception:
-        pass
+    if world == 1:
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh).get(args.workload, {}).get(tkey)
+        except Exception:
+            pass
     pass_bytes = 44.0 if fused else 52.0
     roofline = {"bound": "hbm", "kernel": kernel,
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel, 1 GPU)" if traffic else None,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_kernel, "cg_driver": prof["cg_driver"],
                 "other_kernels": {
                     "stencil_strip_kernel (two-kernel form)": {"ms": prof["cg_stencil"], "GBps": 28.0 * npix / (prof["cg_stencil"] * 1e-3) / 1e9},
@@ -355,6 +487,19 @@ def run_ours(args, rank, world, local):
                 "cg_loop_bytes_per_pixel_pass": pass_bytes}
     ctx.close()
 
+    # ---- the same-size leg of the reference ratio and the other BASELINE configs (N = 1, headline workload only)
+    same_size = extra = None
+    if world == 1 and args.workload == "4k" and not args.no_extras:
+        del sc, out
+        torch.cuda.empty_cache()
+        same_size = time_workload("1k", local, args.albedo, steps=10, warmup=3)
+        same_size["note"] = ("the reference CUDA build runs this size itself (bench.py --impl reference prints its un-scaled "
+                             "measurement under the same key): a same-configuration pair for the speed-up")
+        extra = {"config3_1080p": time_workload("1080p", local, args.albedo, steps=10, warmup=3)}
+        try:
+            extra["config5_batch_1gpu"] = batch_scenes(local, 1, 0, 4, args.albedo)
+        except Exception as ex:                                     # never lose the headline line to an extra
+            extra["config5_batch_1gpu"] = {"error": repr(ex)}
     if rank != 0:
         return
     cb = None
@@ -371,7 +516,7 @@ def run_ours(args, rank, world, local):
                        f"{world} strips of the same scene along the image columns, ghost lines pulled from the neighbours + one 4-value all-reduce per CG pass, "
                        f"exchanged in-kernel over NVLink peer memory" if strips else
                        f"{world} independent replicas, one scene per GPU (value = ms per scene-iteration)"),
-                   "l2": (f"per GPU: image stack {sc['I'].nbytes / 1e9:.2f} GB, CG working set {pass_bytes * npix / 1e6:.0f} MB per pass; "
+                   "l2": (f"per GPU: image stack {stack_gb:.2f} GB, CG working set {pass_bytes * npix / 1e6:.0f} MB per pass; "
                           + ("both exceed the 126 MB L2: no flush needed" if pass_bytes * npix > 126e6 else
                              "the stack exceeds the 126 MB L2, the CG vectors fit it (algorithmic GB/s of the CG may exceed the HBM peak)"))},
         "e2e": {"value": e2e_ms if (strips or world == 1) else e2e_ms / world, "unit": "ms",
@@ -381,6 +526,9 @@ def run_ours(args, rank, world, local):
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cb,
+        "strip_parity": parity,
+        "same_size": same_size,
+        "extra": extra,
         "phases_ms": {k: float(np.mean(v)) for k, v in phases.items()},
         "cg_iters_per_s": float(np.mean(cg_iters)) / (float(np.mean(phases["ms_depth_cg"])) * 1e-3),
         "cg_iters": int(np.mean(cg_iters)),
@@ -403,6 +551,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=1024, help="edge of the square sample the reference CUDA build is timed on")
     ap.add_argument("--ref-cpu", action="store_true", help="reference arm: use the CPU port instead of the reference CUDA build")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the same-size / config 3 / config 5 legs of the N=1 headline run")
     ap.add_argument("--batch-scenes", type=int, default=0,
                     help="> 0: BASELINE config 5 instead of the headline metric -- this many 1080p scenes per GPU, scenes/s")
     ap.add_argument("--parallelism", default="strips", choices=["strips", "replicas"],

@@ -78,6 +78,8 @@ typedef struct srps_timings {
     int cg_iters;                /* depth CG passes executed */
     int albedo_cg_iters[3];
     long long launches;          /* kernels launched by this context since creation */
+    int cg_deferred;             /* fused CG: passes of the last depth solve that measured r.r instead of expanding it */
+    int pad_;
 } srps_timings;
 
 /* Context: replaces cudaSetDevice + handle creation + all one-shot device setup of
@@ -140,7 +142,8 @@ int  srps_timer_stop(srps_ctx* ctx, float* ms);
  * (p <- r + beta p; y <- A p; p.y), [1] = CG update kernel, [2] = lighting stack pass,
  * [3] = stack-projection pass (+ fused albedo / depth coefficients), [4] = fused CG pass (operator +
  * the previous pass's update in one kernel; 0 if sf > 4), [5] = CG driver this context uses
- * (0 operator + update graph, 1 persistent cooperative kernel, 2 fused pass graph).  Needs one completed
+ * (0 operator + update graph, 1 persistent cooperative kernel, 2 fused pass graph, 3 fused passes in one
+ * persistent cooperative kernel).  Needs one completed
  * srps_outer_iteration; leaves the loop state UNDEFINED (re-upload before further use). */
 int  srps_profile_kernels(srps_ctx* ctx, int reps, float* out_ms);
 

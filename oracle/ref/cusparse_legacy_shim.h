@@ -119,13 +119,34 @@ static inline cusparseStatus_t transpose_csr(cusparseHandle_t h, int rows, int c
 }  // namespace srps_shim
 
 /* ---- y = alpha*op(A)*x + beta*y -------------------------------------------------------- */
+namespace srps_shim {
+/* The legacy csrmv needed no host round trip and no allocation.  The generic API wants the true nnz on the host
+   (the reference passes a wrong one at devicecalls.cu:405, and legacy csrmv only trusted the row pointers), so it is
+   read back ONCE per matrix: the CG loop (devicecalls.cu:252-275) multiplies by the same matrix up to 101 times.
+   The entry is keyed by all three array pointers and both dimensions and dropped by every cudaFree of the
+   translation unit (hook at the end of this header) and by every other shim entry point; the SpMV workspace is
+   grow-only.  Round 1's shim did two blocking reads plus a malloc/free per call, which slowed the reference. */
+struct NnzEntry { const int* rowptr; const int* colind; const float* val; int m, n, nnz; };
+static NnzEntry g_nnz = {NULL, NULL, NULL, 0, 0, 0};
+static void* g_spmv_buf = NULL;
+static size_t g_spmv_cap = 0;
+static inline void forget_nnz() { g_nnz.rowptr = NULL; }
+}  // namespace srps_shim
+
 static inline cusparseStatus_t cusparseScsrmv(cusparseHandle_t h, cusparseOperation_t op, int m, int n, int /*nnz*/,
                                               const float* alpha, const cusparseMatDescr_t, const float* val,
                                               const int* rowptr, const int* colind, const float* x,
                                               const float* beta, float* y) {
-    /* the reference passes a wrong nnz at devicecalls.cu:405 (nnz_M for MA); legacy csrmv only
-       trusted the row pointers, so read the true count from them */
-    int nnz = srps_shim::device_int(rowptr + m) - srps_shim::device_int(rowptr);
+    using namespace srps_shim;
+    int nnz;
+    if (g_nnz.rowptr == rowptr && g_nnz.colind == colind && g_nnz.val == val && g_nnz.m == m && g_nnz.n == n) {
+        nnz = g_nnz.nnz;
+    } else {
+        int ends[1] = {0};
+        cudaMemcpy(ends, rowptr + m, sizeof(int), cudaMemcpyDeviceToHost);      /* rowptr[0] == 0: base-zero CSR */
+        nnz = ends[0];
+        g_nnz.rowptr = rowptr; g_nnz.colind = colind; g_nnz.val = val; g_nnz.m = m; g_nnz.n = n; g_nnz.nnz = nnz;
+    }
     cusparseSpMatDescr_t A;
     cusparseDnVecDescr_t vx, vy;
     int xn = (op == CUSPARSE_OPERATION_NON_TRANSPOSE) ? n : m;
@@ -135,11 +156,14 @@ static inline cusparseStatus_t cusparseScsrmv(cusparseHandle_t h, cusparseOperat
     SHIM_CK(cusparseCreateDnVec(&vx, xn, (void*)x, CUDA_R_32F));
     SHIM_CK(cusparseCreateDnVec(&vy, yn, (void*)y, CUDA_R_32F));
     size_t bs = 0;
-    void* buf = NULL;
     SHIM_CK(cusparseSpMV_bufferSize(h, op, alpha, A, vx, beta, vy, CUDA_R_32F, CUSPARSE_SPMV_ALG_DEFAULT, &bs));
-    if (bs) cudaMalloc(&buf, bs);
-    SHIM_CK(cusparseSpMV(h, op, alpha, A, vx, beta, vy, CUDA_R_32F, CUSPARSE_SPMV_ALG_DEFAULT, buf));
-    if (buf) cudaFree(buf);
+    if (bs > g_spmv_cap) {
+        if (g_spmv_buf) cudaFree(g_spmv_buf);
+        g_spmv_buf = NULL;
+        cudaMalloc(&g_spmv_buf, bs);
+        g_spmv_cap = bs;
+    }
+    SHIM_CK(cusparseSpMV(h, op, alpha, A, vx, beta, vy, CUDA_R_32F, CUSPARSE_SPMV_ALG_DEFAULT, g_spmv_buf));
     cusparseDestroySpMat(A);
     cusparseDestroyDnVec(vx);
     cusparseDestroyDnVec(vy);
@@ -153,6 +177,7 @@ static inline cusparseStatus_t cusparseXcsrgemmNnz(cusparseHandle_t h, cusparseO
                                                    const int* colA, const cusparseMatDescr_t, int nnzB,
                                                    const int* rowB, const int* colB, const cusparseMatDescr_t,
                                                    int* rowC, int* nnzTotal) {
+    srps_shim::forget_nnz();
     using namespace srps_shim;
     GemmPending& P = g_gemm;
     P = GemmPending();
@@ -212,6 +237,7 @@ static inline cusparseStatus_t cusparseScsrgemm(cusparseHandle_t h, cusparseOper
                                                 const cusparseMatDescr_t, int nnzB, const float* valB,
                                                 const int* rowB, const int* colB, const cusparseMatDescr_t,
                                                 float* valC, const int* rowC, int* colC) {
+    srps_shim::forget_nnz();
     using namespace srps_shim;
     GemmPending& P = g_gemm;
     if (!P.live || P.m != m || P.n != n || P.k != k) {
@@ -256,6 +282,7 @@ static inline cusparseStatus_t cusparseXcsrgeamNnz(cusparseHandle_t h, int m, in
                                                    const cusparseMatDescr_t dB, int nnzB, const int* rowB,
                                                    const int* colB, const cusparseMatDescr_t dC, int* rowC,
                                                    int* nnzTotal) {
+    srps_shim::forget_nnz();
     size_t bs = 0;
     const float one = 1.f;
     SHIM_CK(cusparseScsrgeam2_bufferSizeExt(h, m, n, &one, dA, nnzA, NULL, rowA, colA, &one, dB, nnzB, NULL, rowB,
@@ -273,6 +300,7 @@ static inline cusparseStatus_t cusparseScsrgeam(cusparseHandle_t h, int m, int n
                                                 const cusparseMatDescr_t dB, int nnzB, const float* valB,
                                                 const int* rowB, const int* colB, const cusparseMatDescr_t dC,
                                                 float* valC, int* rowC, int* colC) {
+    srps_shim::forget_nnz();
     if (!srps_shim::g_geam_buf) {
         fprintf(stderr, "[shim] cusparseScsrgeam without cusparseXcsrgeamNnz\n");
         return CUSPARSE_STATUS_INTERNAL_ERROR;
@@ -289,6 +317,7 @@ static inline cusparseStatus_t cusparseScsr2csc(cusparseHandle_t h, int m, int n
                                                 const int* csrRowPtr, const int* csrColInd, float* cscVal,
                                                 int* cscRowInd, int* cscColPtr, cusparseAction_t action,
                                                 cusparseIndexBase_t) {
+    srps_shim::forget_nnz();
     return srps_shim::transpose_csr(h, m, n, nnz, csrVal, csrRowPtr, csrColInd, cscVal, cscColPtr, cscRowInd, action);
 }
 
@@ -306,3 +335,10 @@ static inline cusparseStatus_t cusparseDestroySolveAnalysisInfo(cusparseSolveAna
 static inline cusparseStatus_t cusparseScsrsv_analysis(cusparseHandle_t, cusparseOperation_t, int, int, const cusparseMatDescr_t, const float*, const int*, const int*, cusparseSolveAnalysisInfo_t) { return CUSPARSE_STATUS_NOT_SUPPORTED; }
 static inline cusparseStatus_t cusparseScsrsv_solve(cusparseHandle_t, cusparseOperation_t, int, const float*, const cusparseMatDescr_t, const float*, const int*, const int*, cusparseSolveAnalysisInfo_t, const float*, float*) { return CUSPARSE_STATUS_NOT_SUPPORTED; }
 static inline cusparseStatus_t cusparseScsrilu0(cusparseHandle_t, cusparseOperation_t, int, const cusparseMatDescr_t, float*, const int*, const int*, cusparseSolveAnalysisInfo_t) { return CUSPARSE_STATUS_NOT_SUPPORTED; }
+
+/* ---- cudaFree hook: a freed matrix must not be found in the csrmv nnz cache --------------- */
+static inline cudaError_t srps_shim_cudaFree(void* p) {
+    srps_shim::forget_nnz();
+    return cudaFree(p);
+}
+#define cudaFree(p) srps_shim_cudaFree((void*)(p))

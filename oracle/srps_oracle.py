@@ -178,12 +178,15 @@ def cg_reference(matvec, x, b, dt=np.float32, max_iter=CG_MAX_ITER, tol=CG_TOL):
     return x, k
 
 
-def cg_fused_reference(matvec, x, b, dt=np.float32, max_iter=CG_MAX_ITER, tol=CG_TOL):
+def cg_fused_reference(matvec, x, b, dt=np.float32, max_iter=CG_MAX_ITER, tol=CG_TOL, defer_rel=1e-6, stats=None):
     """The recurrence of the CUDA path's one-kernel-per-pass CG (csrc/srps_cg.cuh: cg_fused_kernel), restated to
     show that it is the reference's CG (cg_reference above, devicecalls.cu:229-279) in another order of operations:
     pass k first applies the step of pass k-1 (r -= alpha y, x += alpha p), then forms p and y = A p and four dots;
     alpha_k = r.r / p.y with r.r MEASURED; beta_{k+1} = |r_{k+1}|^2 / r.r with |r_{k+1}|^2 = |r - alpha y|^2 expanded
-    from the dots, r.y = p.y - beta (y_prev . p) (A symmetric).  A pass that measures r.r <= tol^2 is void."""
+    from the dots, r.y = p.y - beta (y_prev . p) (A symmetric).  A pass that measures r.r <= tol^2 is void.
+    Guard: when the expansion cancels (|r_{k+1}|^2 < defer_rel * r.r) the next pass slot only applies the pending step
+    and measures r.r; beta then is the reference's r1/r0 of measured norms.  stats (dict) receives the number of
+    deferred passes."""
     f64 = np.float64
     x = x.astype(dt).copy()
     r = b.astype(dt).copy()
@@ -192,9 +195,23 @@ def cg_fused_reference(matvec, x, b, dt=np.float32, max_iter=CG_MAX_ITER, tol=CG
     alpha = dt(0); beta = dt(0)
     p = np.zeros_like(r); y = np.zeros_like(r)
     active = dt(np.dot(r.astype(f64), r.astype(f64))) > tol2
-    while active:
+    deferred = False
+    n_deferred = 0
+    r0 = 0.0
+    slots = max_iter + 1 + 2            # FUSED_SPARE_PASSES
+    while active and slots > 0:
+        slots -= 1
         r = (r - alpha * y).astype(dt)
         x = (x + alpha * p).astype(dt)
+        if deferred:                     # fused_update_only: p, y unchanged, r.r measured
+            S0 = float(np.dot(r.astype(f64), r.astype(f64)))
+            alpha = dt(0)
+            if not (dt(S0) > tol2):
+                break
+            beta = dt(dt(S0) / dt(r0))
+            deferred = False
+            n_deferred += 1
+            continue
         y_prev = y
         p = (r + beta * p).astype(dt)
         y = matvec(p).astype(dt)
@@ -208,10 +225,14 @@ def cg_fused_reference(matvec, x, b, dt=np.float32, max_iter=CG_MAX_ITER, tol=CG
         alpha = dt(dt(S0) / dt(S1))
         S2 = S1 - float(beta) * C
         rr = S0 - 2.0 * float(alpha) * S2 + float(alpha) ** 2 * S3
-        beta = dt(dt(rr) / dt(S0))
+        deferred = not (rr > defer_rel * S0)
+        r0 = S0
+        beta = dt(0) if deferred else dt(dt(rr) / dt(S0))
         k += 1
         active = k <= max_iter
     x = (x + alpha * p).astype(dt)     # the step still pending after the last pass (cg_tail_kernel)
+    if stats is not None:
+        stats["deferred"] = n_deferred
     return x, k
 
 

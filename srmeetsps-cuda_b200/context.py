@@ -164,7 +164,7 @@ class Context:
         self._ck(self.lib.srps_get_timings(self._ctx, C.byref(t)), "srps_get_timings")
         return dict(ms_lighting=t.ms_lighting, ms_albedo=t.ms_albedo, ms_depth=t.ms_depth, ms_normals=t.ms_normals,
                     ms_total=t.ms_total, ms_depth_cg=t.ms_depth_cg, cg_iters=t.cg_iters,
-                    albedo_cg_iters=list(t.albedo_cg_iters), launches=int(t.launches))
+                    albedo_cg_iters=list(t.albedo_cg_iters), launches=int(t.launches), cg_deferred=int(t.cg_deferred))
 
     def synchronize(self):
         self._ck(self.lib.srps_synchronize(self._ctx), "srps_synchronize")
@@ -182,7 +182,7 @@ class Context:
         out = (C.c_float * 6)()
         self._ck(self.lib.srps_profile_kernels(self._ctx, int(reps), out), "srps_profile_kernels")
         return dict(cg_stencil=out[0], cg_update=out[1], lighting_pass=out[2], project_pass=out[3], cg_fused=out[4],
-                    cg_driver={0: "graph", 1: "persistent", 2: "fused"}[int(out[5])])
+                    cg_driver={0: "graph", 1: "persistent", 2: "fused", 3: "persistent_fused"}[int(out[5])])
 
     def apply_depth_operator(self, p):
         p = np.ascontiguousarray(p, dtype=np.float32)

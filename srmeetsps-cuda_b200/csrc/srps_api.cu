@@ -66,7 +66,7 @@ struct srps_ctx {
     int use_persistent_fused = 0;                     // ... in the fused form (one grid barrier per pass; opt-in)
     int use_fused = 0;                                // one kernel per CG pass (cg_fused_kernel)
     int lc_slot = -1;                                 // this context's slot of the constant-bank lighting constants (c_lc)
-    unsigned long long* sync_words = nullptr;         // [0] grid barrier counter, [1] world generation, [2..5] world totals (as double)
+    unsigned long long* sync_words = nullptr;         // [0] grid barrier counter, [1] world generation, [2..9] world totals (as double)
     long long n4 = 0;
     cudaGraphExec_t cg_graph = nullptr;
     int use_graph = 1;
@@ -162,6 +162,31 @@ extern "C" void srps_ctx_destroy(srps_ctx* ctx) {
     delete ctx;
 }
 
+// Kernel instances by sf (the warp-strip kernels are templated on it): occupancy is queried for, and the cooperative
+// grid sized by, the instance that is actually launched.
+static const void* fn_strip_iter(int sf) {
+    return sf == 1 ? (const void*)stencil_strip_kernel<MODE_ITER, 1> : (sf == 2 ? (const void*)stencil_strip_kernel<MODE_ITER, 2>
+                                                                                : (const void*)stencil_strip_kernel<MODE_ITER, 4>);
+}
+static const void* fn_fused(int sf, bool first) {
+    if (first) return sf == 1 ? (const void*)cg_fused_kernel<1, true> : (sf == 2 ? (const void*)cg_fused_kernel<2, true> : (const void*)cg_fused_kernel<4, true>);
+    return sf == 1 ? (const void*)cg_fused_kernel<1, false> : (sf == 2 ? (const void*)cg_fused_kernel<2, false> : (const void*)cg_fused_kernel<4, false>);
+}
+static const void* fn_persistent(int sf) {
+    return sf == 1 ? (const void*)cg_persistent_kernel<1> : (sf == 2 ? (const void*)cg_persistent_kernel<2> : (const void*)cg_persistent_kernel<4>);
+}
+static const void* fn_persistent_fused(int sf, bool world) {
+    if (world) return sf == 1 ? (const void*)cg_persistent_fused_kernel<1, 2> : (sf == 2 ? (const void*)cg_persistent_fused_kernel<2, 2>
+                                                                                           : (const void*)cg_persistent_fused_kernel<4, 2>);
+    return sf == 1 ? (const void*)cg_persistent_fused_kernel<1, 1> : (sf == 2 ? (const void*)cg_persistent_fused_kernel<2, 1>
+                                                                              : (const void*)cg_persistent_fused_kernel<4, 1>);
+}
+static int occupancy(const void* fn, int threads) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return occ;
+}
+
 static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     const int h = prob->h, w = prob->w, sf = prob->sf;
     ctx->prob = *prob;
@@ -190,6 +215,7 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
                 jmin = std::min(jmin, j); jmax = std::max(jmax, j);
             }
     if (npix == 0) return fail(ctx, SRPS_E_INVALID, "empty mask");
+    // (a strip without mask pixels is rejected below, once the owned columns are known)
     Grid& g = ctx->g;
     g.sf = sf;
     g.ib0 = imin / sf * sf; g.jb0 = jmin / sf * sf;
@@ -214,6 +240,7 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
                 lr_before += all;
             }
         ctx->pix0 = before; ctx->lr0 = lr_before;
+        if (npix == 0) return fail(ctx, SRPS_E_INVALID, "this rank's strip holds no mask pixel (cut the strips over the mask's column range)");
     }
     g.nx = ib1 - g.ib0; g.ny = jb1 - g.jb0;
     g.pitch = round_up(g.nx + 1, 32);
@@ -333,44 +360,47 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     {   // warp-strip operator (sf <= 4): strips of 30 float4 columns x chunks of lines, one warp each
         const char* si = getenv("SRPS_STENCIL");
         ctx->use_strip = (sf <= 4) && (!(si && strcmp(si, "tile") == 0) || ctx->world > 1);
+        const int sfk = sf <= 4 ? sf : 4;                  // kernel instance (sf 8 / 16 never launch the strip kernels)
         const int nq = (g.nx + 3) / 4;
         ctx->strip_n = (nq + SW_COLS - 1) / SW_COLS;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stencil_strip_kernel<MODE_ITER, 4>, SW_NT, 0));
-        {
-            int occ_f = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, cg_fused_kernel<4, false>, SW_NT, 0));
-            occ = std::max(1, std::min(occ, occ_f));      // one strip geometry for both CG forms
+        // persistent CG (one cooperative launch per solve): every block must be resident at once
+        int coop = 0;
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+        const char* cgm = getenv("SRPS_CG");
+        // Measured (round 1): a persistent single-launch CG wins on small single-GPU scenes (two-barrier form: Mitten 1.35 vs
+        // 1.52 ms, 1080p 2.62 vs 2.95 ms per outer iteration; fused one-barrier form: Mitten 1.11 ms) and loses at 4096^2
+        // (17.7 vs 15.4 ms of CG).  Default: below 3 M pixels PER GPU the persistent fused form (cg_persistent_fused_kernel;
+        // with a strip partition its barrier carries the cross-GPU reduction), otherwise one fused kernel per pass
+        // (cg_fused_kernel; 4096^2: 14.1 ms against 15.5 ms for operator + update, and one cross-GPU reduction per pass
+        // instead of two).  SRPS_CG = persistent_fused | persistent | fused | graph overrides.
+        const bool small = npix < 3000000;
+        const bool want_pf = cgm ? strcmp(cgm, "persistent_fused") == 0 : small;
+        const bool want_p = cgm && strcmp(cgm, "persistent") == 0;
+        int occ_p = 0;
+        if (want_p && ctx->use_strip && coop && ctx->world == 1) {
+            occ_p = occupancy(fn_persistent(sfk), SW_NT);
+            ctx->use_persistent = occ_p > 0;
         }
-        const int warps = ctx->sm_count * std::max(1, occ) * (SW_NT / 32);
+        if (want_pf && ctx->use_strip && coop) {
+            occ_p = occupancy(fn_persistent_fused(sfk, ctx->world > 1), SW_NT);
+            ctx->use_persistent_fused = ctx->use_persistent = occ_p > 0;
+        }
+        ctx->use_fused = ctx->use_strip && !ctx->use_persistent && !(cgm && strcmp(cgm, "graph") == 0);
+        // one strip geometry for all CG forms of this context: the occupancy of the instances that can be launched
+        // (the <sf> instances, not a representative: a cooperative grid sized by another instance's occupancy could
+        //  exceed what is resident at once)
+        occ = std::max(1, std::min({occupancy(fn_strip_iter(sfk), SW_NT), occupancy(fn_fused(sfk, false), SW_NT),
+                                    occupancy(fn_fused(sfk, true), SW_NT), ctx->use_persistent ? occ_p : 1 << 20}));
+        const int warps = ctx->sm_count * occ * (SW_NT / 32);
         int cl = (int)(((long long)g.ny * ctx->strip_n + warps - 1) / warps);
         cl = std::min(256, std::max(8, round_up(cl, SW_G)));
         ctx->strip_cl = cl;
         ctx->strip_chunks = (g.ny + cl - 1) / cl;
         const int nitems = ctx->strip_n * ctx->strip_chunks;
-        ctx->grid_strip = std::min((nitems + SW_NT / 32 - 1) / (SW_NT / 32), ctx->sm_count * std::max(1, occ));
-        // persistent CG (one cooperative launch per solve): every block must be resident at once
-        int coop = 0, occ_p = 0;
-        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, cg_persistent_kernel<4>, SW_NT, 0));
-        const char* cgm = getenv("SRPS_CG");
-        // Measured (round 1): a persistent single-launch CG wins on small single-GPU scenes (two-barrier form: Mitten 1.35 vs
-        // 1.52 ms, 1080p 2.62 vs 2.95 ms per outer iteration; fused one-barrier form: Mitten 1.11 ms), loses at 4096^2
-        // (17.7 vs 15.4 ms of CG) and does not help the strip partition (2 GPUs: 11.9 vs 10.2 ms).
-        // Default: below 3 M pixels on one GPU the persistent fused form (cg_persistent_fused_kernel), otherwise one fused
-        // kernel per pass (cg_fused_kernel; 4096^2: 14.1 ms against 15.5 ms for operator + update, and one cross-GPU
-        // reduction per pass instead of two).  SRPS_CG = persistent_fused | persistent | fused | graph overrides.
-        const bool small = ctx->world == 1 && npix < 3000000;
-        const bool want_pf = cgm ? strcmp(cgm, "persistent_fused") == 0 : small;
-        const bool want_p = cgm && strcmp(cgm, "persistent") == 0;
-        ctx->use_persistent = ctx->use_strip && coop && occ_p > 0 && ctx->world == 1 && want_p;
-        if (want_pf && ctx->world == 1 && ctx->use_strip && coop) {
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, cg_persistent_fused_kernel<4>, SW_NT, 0));
-            ctx->use_persistent_fused = ctx->use_persistent = occ_p > 0;
-        }
-        ctx->use_fused = ctx->use_strip && !ctx->use_persistent && !(cgm && strcmp(cgm, "graph") == 0);
-        ctx->grid_persistent = std::min(ctx->grid_strip, ctx->sm_count * std::max(1, occ_p));
-        CK(cudaMalloc(&ctx->sync_words, 8 * sizeof(unsigned long long)));
-        CK(cudaMemsetAsync(ctx->sync_words, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        ctx->grid_strip = std::min((nitems + SW_NT / 32 - 1) / (SW_NT / 32), ctx->sm_count * occ);
+        ctx->grid_persistent = ctx->grid_strip;            // <= sm_count * occ_p: all blocks co-resident
+        CK(cudaMalloc(&ctx->sync_words, 16 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(ctx->sync_words, 0, 16 * sizeof(unsigned long long), ctx->stream));
     }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_update_kernel, CG_NT, 0));
     ctx->grid_update = (int)std::min<long long>((ctx->n4 + CG_NT - 1) / CG_NT, (long long)ctx->sm_count * std::max(1, occ));
@@ -800,6 +830,7 @@ static void launch_fused_tail(srps_ctx* ctx) {
 }
 
 static int launch_cg_fused(srps_ctx* ctx, StencilArgs sa, int passes) {
+    passes += FUSED_SPARE_PASSES;            // slots for deferred (update-only) passes; idle ones exit on !active
     for (int k = 0; k < passes; k++) {
         set_fused_pass(ctx, sa, k);
         launch_fused_pass(ctx, sa, k == 0);
@@ -847,18 +878,18 @@ extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
         pa.bar = ctx->sync_words; pa.world_gen = ctx->sync_words + 1; pa.world_tot = (double*)(ctx->sync_words + 2);
         pa.rr[0] = ctx->r; pa.rr[1] = ctx->r2; pa.yy[0] = ctx->y; pa.yy[1] = ctx->y2;
         pa.part[0] = ctx->partials; pa.part[1] = ctx->partials + 4ll * ctx->grid_persistent;
+        peer_boundary_lines(ctx, ctx->r, pa.r_prev[0], pa.r_next[0]);
+        peer_boundary_lines(ctx, ctx->r2, pa.r_prev[1], pa.r_next[1]);
+        peer_boundary_lines(ctx, ctx->y, pa.y_prev[0], pa.y_next[0]);
+        peer_boundary_lines(ctx, ctx->y2, pa.y_prev[1], pa.y_next[1]);
         CK(cudaMemsetAsync(ctx->sync_words, 0, 2 * sizeof(unsigned long long), ctx->stream));
         void* kargs[] = {&pa};
-        const void* fn = ctx->g.sf == 1 ? (const void*)cg_persistent_kernel<1>
-                         : (ctx->g.sf == 2 ? (const void*)cg_persistent_kernel<2> : (const void*)cg_persistent_kernel<4>);
-        if (ctx->use_persistent_fused)
-            fn = ctx->g.sf == 1 ? (const void*)cg_persistent_fused_kernel<1>
-                 : (ctx->g.sf == 2 ? (const void*)cg_persistent_fused_kernel<2> : (const void*)cg_persistent_fused_kernel<4>);
+        const void* fn = ctx->use_persistent_fused ? fn_persistent_fused(ctx->g.sf, ctx->world > 1) : fn_persistent(ctx->g.sf);
         CK(cudaLaunchCooperativeKernel(fn, dim3(ctx->grid_persistent), dim3(SW_NT), kargs, 0, ctx->stream));
         ctx->launches++;
     } else if (getenv("SRPS_TRACE")) {
         // debugging aid: one pass at a time, CG scalars printed after each (no graph)
-        for (int k = 0; k < passes; k++) {
+        for (int k = 0; k < passes + (ctx->use_fused ? FUSED_SPARE_PASSES : 0); k++) {
             StencilArgs s1 = sa; UpdateArgs u1 = ua;
             if (ctx->use_fused) {
                 set_fused_pass(ctx, s1, k);
@@ -870,8 +901,9 @@ extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
             }
             CK(cudaMemcpyAsync(ctx->h_sc, ctx->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
-            fprintf(stderr, "[srps rank %d] pass %3d: r1 %.6e r0 %.6e p.Ap %.6e alpha %.6e beta %.6e k %d active %d\n", ctx->rank, k,
-                    ctx->h_sc[0].r1, ctx->h_sc[0].r0, ctx->h_sc[0].dot, ctx->h_sc[0].alpha, ctx->h_sc[0].beta, ctx->h_sc[0].k, ctx->h_sc[0].active);
+            fprintf(stderr, "[srps rank %d] pass %3d: r1 %.6e r0 %.6e p.Ap %.6e alpha %.6e beta %.6e k %d active %d defer %d\n", ctx->rank, k,
+                    ctx->h_sc[0].r1, ctx->h_sc[0].r0, ctx->h_sc[0].dot, ctx->h_sc[0].alpha, ctx->h_sc[0].beta, ctx->h_sc[0].k, ctx->h_sc[0].active,
+                    ctx->h_sc[0].defer);
             if (!ctx->h_sc[0].active) break;
         }
         if (ctx->use_fused) launch_fused_tail(ctx);
@@ -887,7 +919,7 @@ extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
             CK(cudaGraphDestroy(graph));
         }
         CK(cudaGraphLaunch(ctx->cg_graph, ctx->stream));
-        ctx->launches += ctx->use_fused ? passes + 1ll : 2ll * passes;
+        ctx->launches += ctx->use_fused ? passes + FUSED_SPARE_PASSES + 1ll : 2ll * passes;
     } else {
         if (ctx->use_fused) launch_cg_fused(ctx, sa, passes); else launch_cg_iterations(ctx, sa, ua, passes);
         CK(cudaGetLastError());
@@ -907,6 +939,7 @@ extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
     CK(cudaMemcpyAsync(ctx->h_sc, ctx->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->tm.cg_iters = ctx->h_sc[0].k;
+    ctx->tm.cg_deferred = ctx->h_sc[0].n_defer;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
     ctx->tm.ms_depth_cg = ms;
@@ -1028,6 +1061,7 @@ extern "C" int srps_profile_kernels(srps_ctx* ctx, int reps, float* out_ms) {
     // keep the CG kernels active for the whole measurement with fixed, benign scalars
     CgScalars sc = ctx->h_sc[0];
     sc.active = 1; sc.beta = 0.5f; sc.alpha = 1e-3f; sc.r1 = 1.0; sc.r0 = 1.0; sc.k = 0; sc.max_iter = 1 << 30; sc.tol2 = 0.f;
+    sc.defer = 0; sc.profile = 1;            // the fused pass keeps these scalars (no deferred passes inside the timing)
     CgScalars* h = ctx->h_sc;
     const CgScalars saved = h[0];
     h[0] = sc;
@@ -1087,7 +1121,7 @@ extern "C" int srps_profile_kernels(srps_ctx* ctx, int reps, float* out_ms) {
         CK(cudaStreamSynchronize(ctx->stream));
         if (!h[3].active) out_ms[4] = 0.f;        // the recurrence died on this state: no valid timing (bench.py reports 0)
     }
-    out_ms[5] = ctx->use_persistent ? 1.f : (ctx->use_fused ? 2.f : 0.f);
+    out_ms[5] = ctx->use_persistent_fused ? 3.f : (ctx->use_persistent ? 1.f : (ctx->use_fused ? 2.f : 0.f));
     // restore the reference CG parameters
     h[0] = saved;
     CK(cudaMemcpyAsync(ctx->sc, h, sizeof(CgScalars), cudaMemcpyHostToDevice, ctx->stream));

@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(CG_NT, 3) stencil_kernel(const StencilArgs a) 
         if (threadIdx.x == 0) {
             CgScalars* s = a.sc;
             if (MODE == MODE_INIT) {                 // r1 = b.b ; k = 0          devicecalls.cu:242-252
-                s->r1 = total; s->r0 = 0.0; s->k = 0; s->beta = 0.f; s->alpha = 0.f;
+                s->r1 = total; s->r0 = 0.0; s->k = 0; s->beta = 0.f; s->alpha = 0.f; s->defer = 0; s->n_defer = 0;
                 s->active = ((float)total > s->tol2) && (0 <= s->max_iter);
             } else {                                 // alpha = r1 / (p.Ap)       devicecalls.cu:268-269
                 s->dot = total;
@@ -375,7 +375,9 @@ __device__ __forceinline__ LineQ line_q(const LightConsts& lc, float fx, float f
 
 // One application of the operator over this block's share of the (strip, chunk) items.  `a.p_in` / `a.p_out`
 // are the ping-pong planes of this pass; returns this thread's partial of p.y (MODE_ITER).
-template <int MODE, int SF>
+// COH: how planes that are rewritten between passes (r, y, p) are loaded -- 0: one launch per pass, read-only path;
+// 1 / 2: inside a single-launch persistent CG (ld4_coh, srps_common.cuh).  types and w never change during a solve.
+template <int MODE, int SF, int COH = 0>
 __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightConsts& lc, float beta, float alpha = 0.f,
                                              double* extra = nullptr /* FUSED: r.r, y_in.p, y.y */) {
     static_assert(MODE == MODE_ITER || MODE == MODE_APPLY || MODE == MODE_FUSED || MODE == MODE_FUSED0,
@@ -405,10 +407,13 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
         // (a) a lane beyond the line pitch -- a non-writing halo lane whose only consumer is the pad pixel of the last
         // valid float4 (type 0, forced to 0), or (b) a line beyond the guard/ghost line ny -- never an output line, never
         // the lower neighbour of one, and outside every sf x sf block of an output line (ny is a multiple of sf).
-        // Read-only operands use the non-coherent path (nothing read here is written here: the new p goes to the other
-        // ping-pong plane).  Strip partition: r on a ghost line (j = -1 / ny) is read in place from the neighbour's
-        // boundary line over NVLink (pointer select).  Peer lines may sit in this SM's L1 only within one launch; every
-        // pass is its own launch (the single-launch persistent CG is not used with a strip partition).
+        // With one launch per pass (COH = 0) the operands are read-only for the whole kernel and use the non-coherent
+        // path (the new p, r, y go to the other ping-pong planes).  Inside a single-launch persistent CG the same planes
+        // are rewritten every pass, so r, y, p use coherent loads there (COH = 1; PTX defines .nc only for data that is
+        // read-only for the whole kernel).  Strip partition: r / y on a ghost line (j = -1 / ny) are read in place from
+        // the neighbour's boundary line over NVLink (pointer select); peer lines are cached in this SM's L1 only, which
+        // is invalidated at a kernel boundary but not by the in-kernel barrier of the persistent form -> COH = 2 reads
+        // r and y at system scope.
         auto load_pn = [&](int j) -> float4 {
             const bool ok = colok && j <= ny;                      // line ny is the zero guard (or ghost) line
             const long long off = ok ? (long long)j * pitch + x : 0;
@@ -416,7 +421,7 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
                 const float* rs = a.r + off;
                 rs = (ok && j < 0 && a.r_prev_line) ? a.r_prev_line + x : rs;
                 rs = (ok && j == ny && a.r_next_line) ? a.r_next_line + x : rs;
-                const float4 r4 = ldg4(rs), p4 = ldg4(a.p_in + off);
+                const float4 r4 = ld4_coh<COH>(rs), p4 = ld4_coh<(COH ? 1 : 0)>(a.p_in + off);      // p is never read from a peer
                 return make_float4(r4.x + beta * p4.x, r4.y + beta * p4.y, r4.z + beta * p4.z, r4.w + beta * p4.w);
             }
             return ldg4(a.vin + off);
@@ -429,13 +434,13 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
             const float* rs = a.r + off;
             rs = (ok && j < 0 && a.r_prev_line) ? a.r_prev_line + x : rs;
             rs = (ok && j == ny && a.r_next_line) ? a.r_next_line + x : rs;
-            const float4 r4 = ldg4(rs);
+            const float4 r4 = ld4_coh<COH>(rs);
             if (MODE == MODE_FUSED0) { rn = r4; pin = f4zero(); ypn = 0.f; return r4; }       // first pass: p = r
             const float* ys = a.y_in + off;
             ys = (ok && j < 0 && a.y_prev_line) ? a.y_prev_line + x : ys;
             ys = (ok && j == ny && a.y_next_line) ? a.y_next_line + x : ys;
-            const float4 y4 = ldg4(ys);
-            pin = ldg4(a.p_in + off);
+            const float4 y4 = ld4_coh<COH>(ys);
+            pin = ld4_coh<(COH ? 1 : 0)>(a.p_in + off);
             rn = make_float4(r4.x - alpha * y4.x, r4.y - alpha * y4.y, r4.z - alpha * y4.z, r4.w - alpha * y4.w);
             const float4 pn = make_float4(rn.x + beta * pin.x, rn.y + beta * pin.y, rn.z + beta * pin.z, rn.w + beta * pin.w);
             ypn = (y4.x * pn.x + y4.y * pn.y) + (y4.z * pn.z + y4.w * pn.w);      // (A p_in).p : the conjugacy defect, see cg_fused_kernel
@@ -665,6 +670,11 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_update_kernel(const UpdateArgs a)
 // so only beta rests on the expanded norm, for one pass; the next pass measures r.r again (no drift).  The stop test
 // r.r > tol^2 (devicecalls.cu:252) uses the MEASURED value one pass late: a pass that finds S0 <= tol^2 is void -- it has
 // already applied the previous step to z, cancels its own, and leaves k where the reference's loop would.
+// Guard: the expansion cancels when one step removes almost the whole residual (|r_{k+1}|^2 < 1e-6 r.r: early
+// convergence, e.g. sf = 1 scenes where Kt K = I) -- its absolute error is ~1e-7 r.r, so beta would be noise, or
+// negative.  Such a pass sets `defer`; the next pass slot then only applies the pending step (r, z; p and y are copied
+// to the other planes so the ping-pong stays in phase), MEASURES r.r -- exactly the reference's r1 -- and forms beta
+// from it; k does not advance, the solve gets two spare slots for it (fused_update_only).
 // Algorithmic traffic: 44 B/pixel/pass (r, y, p, z, 3 w read; r, p, y, z written) against 52 for the two-kernel form.
 // cg_tail_kernel applies the step that is still pending after the last pass.
 // ---------------------------------------------------------------------------------------------
@@ -704,6 +714,35 @@ __device__ __forceinline__ bool grid_reduce_last4(const double (&v)[4], double* 
     return true;
 }
 
+constexpr double FUSED_DEFER_REL = 1e-6;     // expanded |r_{k+1}|^2 below this fraction of r.r: measure instead
+constexpr int FUSED_SPARE_PASSES = 2;        // pass slots a solve has for deferred (update-only) passes
+
+// Deferred pass (see the header comment): r_out = r - alpha y ; z += alpha p ; p_out = p ; y_out = y ; returns this
+// thread's share of |r_out|^2.  Element-wise over the owned lines; p is copied on the two ghost / guard lines as well
+// (strip partition: the neighbours' p there is kept redundantly; r and y ghosts are pulled, not stored).
+template <int COH>
+__device__ __forceinline__ double fused_update_only(const StencilArgs& a, float alpha) {
+    const long long q = a.g.pitch / 4;
+    const long long lo = -q, hi = (long long)(a.g.ny + 1) * q, own = (long long)a.g.ny * q;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    double s = 0.0;
+    for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+        const float4 p4 = ld4_coh<(COH ? 1 : 0)>(a.p_in + 4 * i);
+        st4(a.p_out + 4 * i, p4);
+        if (i >= 0 && i < own) {
+            const float4 r4 = ld4_coh<(COH ? 1 : 0)>(a.r + 4 * i), y4 = ld4_coh<(COH ? 1 : 0)>(a.y_in + 4 * i);
+            float4 x4 = ld4(a.x + 4 * i);
+            const float4 rn = make_float4(r4.x - alpha * y4.x, r4.y - alpha * y4.y, r4.z - alpha * y4.z, r4.w - alpha * y4.w);
+            x4.x += alpha * p4.x; x4.y += alpha * p4.y; x4.z += alpha * p4.z; x4.w += alpha * p4.w;
+            st4(a.r_out + 4 * i, rn);
+            st4(a.y + 4 * i, y4);
+            st4(a.x + 4 * i, x4);
+            s += (double)((rn.x * rn.x + rn.y * rn.y) + (rn.z * rn.z + rn.w * rn.w));
+        }
+    }
+    return s;
+}
+
 #ifndef SRPS_FUSED_MINB
 #define SRPS_FUSED_MINB 3
 #endif
@@ -714,28 +753,46 @@ __global__ void __launch_bounds__(SW_NT, SRPS_FUSED_MINB) cg_fused_kernel(const 
     if (!a.sc->active) return;
     const float beta = FIRST ? 0.f : a.sc->beta;
     const float alpha = FIRST ? 0.f : a.sc->alpha;          // the step of the previous pass, still pending
-    const LightConsts& lc = c_lc[a.lc_slot];
-    double ex[3];
-    const double py = strip_pass<FIRST ? MODE_FUSED0 : MODE_FUSED, SF>(a, lc, beta, alpha, ex);
-    const double v[4] = {ex[0], py, ex[1], ex[2]};
+    const bool deferred = !FIRST && a.sc->defer != 0;       // uniform over the grid: written by the previous launch
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    if (deferred) {
+        v[0] = fused_update_only<0>(a, alpha);
+    } else {
+        const LightConsts& lc = c_lc[a.lc_slot];
+        double ex[3];
+        v[1] = strip_pass<FIRST ? MODE_FUSED0 : MODE_FUSED, SF>(a, lc, beta, alpha, ex);
+        v[0] = ex[0]; v[2] = ex[1]; v[3] = ex[2];
+    }
     if (!grid_reduce_last4<SW_NT>(v, a.partials, a.ticket, wsm, tot)) return;
-    peer_allreduce_small<SW_NT, 4>(a.comm, tot, false);
+    // strip partition: the neighbours pull their ghost lines of r_out / y out of this rank's planes in the next pass
+    peer_allreduce_small<SW_NT, 4>(a.comm, tot, a.comm.world > 1);
     if (threadIdx.x == 0) {
         CgScalars* s = a.sc;
         const double S0 = tot[0], S1 = tot[1], S3 = tot[3];
         const double S2 = S1 - (double)beta * tot[2];          // r.y, see the header comment
-        if (!((float)S0 > s->tol2)) {            // the reference left its loop before this pass (devicecalls.cu:252)
+        if (s->profile) {                        // srps_profile_kernels: scalars stay as the host set them
+            s->k += 1;
+        } else if (!((float)S0 > s->tol2)) {     // the reference left its loop before this pass (devicecalls.cu:252)
             s->r1 = S0;
             s->alpha = 0.f;                      // nothing pending: the previous step went into z above
             s->active = 0;
+            s->defer = 0;
+        } else if (deferred) {                   // S0 is the measured r1 of the reference's loop
+            s->beta = (float)S0 / (float)s->r0;                                    // devicecalls.cu:262
+            s->r1 = S0;
+            s->alpha = 0.f;                      // applied above
+            s->defer = 0;
+            s->n_defer += 1;
         } else {
             const float al = (float)S0 / (float)S1;                                // devicecalls.cu:269
             const double rr = S0 - 2.0 * (double)al * S2 + (double)al * (double)al * S3;
+            const bool cancelled = !(rr > FUSED_DEFER_REL * S0);                   // also catches a non-finite rr
             s->dot = S1;
             s->alpha = al;
             s->r0 = S0;
             s->r1 = rr;
-            s->beta = (float)rr / (float)S0;                                       // devicecalls.cu:262
+            s->beta = cancelled ? 0.f : (float)rr / (float)S0;                     // devicecalls.cu:262
+            s->defer = cancelled ? 1 : 0;
             s->k += 1;
             s->plane = a.plane;
             s->active = (s->k <= s->max_iter);                                     // devicecalls.cu:252 (k part)
@@ -782,8 +839,12 @@ struct PersistentArgs {
     unsigned long long* bar;        // grid barrier counter, zero on entry
     double* part[2];                // per-block partials: the two reductions of a pass (gridDim.x doubles each) / fused form:
                                     // the four dots of a pass, buffers alternating between passes (4 * gridDim.x doubles each)
-    double* world_tot;              // [4] world totals published by block 0 (strip partition)
+    double* world_tot;              // two-barrier form: [4] world totals published by block 0, slot gen & 3;
+                                    // fused form: [2][4] the four world totals of a pass, slot gen & 1 (strip partition)
     unsigned long long* world_gen;  // generation of the last published world total
+    // strip partition, fused form: the neighbours' boundary lines of the two r and the two y planes (read in place)
+    const float* r_prev[2]; const float* r_next[2];
+    const float* y_prev[2]; const float* y_next[2];
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
@@ -860,7 +921,7 @@ __global__ void __launch_bounds__(SW_NT, SRPS_STRIP_MINB) cg_persistent_kernel(c
         // ---- p <- r + beta p ; y <- A p ; p.y                         devicecalls.cu:256-268
         st.p_in = a.pp[pass & 1];
         st.p_out = a.pp[(pass + 1) & 1];
-        const double dot = grid_allreduce(a, strip_pass<MODE_ITER, SF>(st, lc, beta), 0, gen, red, false);
+        const double dot = grid_allreduce(a, strip_pass<MODE_ITER, SF, 1>(st, lc, beta), 0, gen, red, false);
         const float alpha = (float)r1 / (float)dot;                      // devicecalls.cu:269
         // ---- x += alpha p ; r -= alpha y ; r.r                          devicecalls.cu:270-274
         double acc = 0.0;
@@ -887,14 +948,22 @@ __global__ void __launch_bounds__(SW_NT, SRPS_STRIP_MINB) cg_persistent_kernel(c
 
 // ---------------------------------------------------------------------------------------------
 // Persistent CG, fused form: the passes of cg_fused_kernel inside ONE cooperative launch -- one grid barrier per
-// pass (it carries the four dots) instead of the two of cg_persistent_kernel.  Single GPU only.  Every block
-// derives alpha / beta / active from the same rank-ordered totals, so all blocks take the same decisions; the
-// step still pending when the loop ends is applied by all blocks after the last barrier.  Measured (round 1, Mitten,
-// 148 600 pixels): 1.11 ms per outer iteration against 1.35 ms for cg_persistent_kernel.
+// pass (it carries the four dots) instead of the two of cg_persistent_kernel.  Every block derives alpha / beta /
+// active from the same rank-ordered totals, so all blocks (and, with a strip partition, all ranks) take the same
+// decisions; the step still pending when the loop ends is applied by all blocks after the last barrier.
+// Measured (round 1, Mitten, 148 600 pixels): 1.11 ms per outer iteration against 1.35 ms for cg_persistent_kernel.
+//
+// Single GPU: every block waits for the arrival counter and sums all partials itself (fixed order, no broadcast hop).
+// Strip partition (world > 1): the LAST block to arrive sums the partials, exchanges the four rank totals with the
+// peers (peer_allreduce_small: one NVLink store per peer and word, system-scope release/acquire around it) and
+// publishes the world totals under a generation word; everybody else spins on that word.  The barrier therefore also
+// orders this rank's r / y boundary lines before the neighbours' next pass, which reads them in place (COH = 2).
 // ---------------------------------------------------------------------------------------------
+template <bool WORLD>
 __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double (&v)[4], int which, unsigned long long& gen,
                                                 double* wsm /* [SW_NT/32][4] */, double* s_tot /* [4] */) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ int s_islast;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const double s = warp_sum(v[i]);
@@ -908,62 +977,104 @@ __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double 
         a.part[which][(long long)blockIdx.x * 4 + threadIdx.x] = b;
     }
     __syncthreads();
+    const unsigned long long target = (gen + 1ull) * gridDim.x;
     if (threadIdx.x == 0) {
         __threadfence();
-        atomicAdd(a.bar, 1ull);
-        const unsigned long long target = (gen + 1ull) * gridDim.x;
-        while (ld_acquire_gpu(a.bar) < target) { }
+        const unsigned long long t = atomicAdd(a.bar, 1ull);
+        if (WORLD) {
+            s_islast = (t == target - 1ull);
+        } else {
+            while (ld_acquire_gpu(a.bar) < target) { }
+        }
     }
     __syncthreads();
     gen += 1ull;
-    {   // warp `wid` sums value `wid` over the blocks in a fixed order (SW_NT / 32 == 4 warps)
+    if (!WORLD || s_islast) {
+        // warp `wid` sums value `wid` over the blocks in a fixed order (SW_NT / 32 == 4 warps)
+        if (WORLD) __threadfence();
         double t = 0.0;
         for (int i = lane; i < (int)gridDim.x; i += 32) t += __ldcg(a.part[which] + (long long)i * 4 + wid);
         t = warp_sum(t);
         if (lane == 0) s_tot[wid] = t;
+        __syncthreads();
+        if (WORLD) {
+            peer_allreduce_small<SW_NT, 4>(a.st.comm, s_tot, true);
+            if (threadIdx.x < 4) a.world_tot[(gen & 1ull) * 4 + threadIdx.x] = s_tot[threadIdx.x];
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.world_gen), "l"(gen) : "memory");
+            }
+        }
+    } else {
+        if (threadIdx.x == 0) { while (ld_acquire_gpu(a.world_gen) < gen) { } }
+        __syncthreads();
+        if (threadIdx.x < 4) s_tot[threadIdx.x] = __ldcg(a.world_tot + (gen & 1ull) * 4 + threadIdx.x);
+        __syncthreads();
     }
-    __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; i++) v[i] = s_tot[i];
     __syncthreads();
 }
 
-template <int SF>
+template <int SF, int COH>
 __global__ void __launch_bounds__(SW_NT, SRPS_FUSED_MINB) cg_persistent_fused_kernel(const PersistentArgs a) {
     static_assert(SW_NT / 32 == 4, "one warp per dot in grid_allreduce4");
+    static_assert(COH == 1 || COH == 2, "planes are rewritten inside this launch: coherent loads");
+    constexpr bool WORLD = (COH == 2);
     __shared__ double wsm[(SW_NT / 32) * 4];
     __shared__ double s_tot[4];
     CgScalars* sc = a.st.sc;
-    if (!sc->active) return;                         // r.r <= tol^2 already after the residual kernel (uniform)
+    if (!sc->active) return;                         // r.r <= tol^2 already after the residual kernel (uniform, also over the ranks)
     const LightConsts& lc = c_lc[a.st.lc_slot];
     const float tol2 = sc->tol2;
     const int max_iter = sc->max_iter;
     double r1 = sc->r1, r0 = 0.0;
     float alpha = 0.f, beta = 0.f;                   // alpha: the step of the previous pass, still pending
     int k = 0, plane = 0;
+    bool deferred = false;
+    int n_defer = 0;
     unsigned long long gen = 0ull;
     StencilArgs st = a.st;
     st.x = a.x;
-    for (int pass = 0; pass < a.passes; pass++) {
+    for (int pass = 0; pass < a.passes + FUSED_SPARE_PASSES; pass++) {
         st.r = a.rr[pass & 1];   st.r_out = a.rr[(pass + 1) & 1];
         st.y_in = a.yy[pass & 1]; st.y = a.yy[(pass + 1) & 1];
         st.p_in = a.pp[pass & 1]; st.p_out = a.pp[(pass + 1) & 1];
-        double ex[3];
-        const double py = (pass == 0) ? strip_pass<MODE_FUSED0, SF>(st, lc, 0.f, 0.f, ex)
-                                      : strip_pass<MODE_FUSED, SF>(st, lc, beta, alpha, ex);
-        double v[4] = {ex[0], py, ex[1], ex[2]};
-        grid_allreduce4(a, v, pass & 1, gen, wsm, s_tot);
+        if (WORLD) {             // the neighbours' boundary lines of this pass's r / y planes
+            st.r_prev_line = a.r_prev[pass & 1]; st.r_next_line = a.r_next[pass & 1];
+            st.y_prev_line = a.y_prev[pass & 1]; st.y_next_line = a.y_next[pass & 1];
+        }
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        if (deferred) {                              // see cg_fused_kernel: apply the step, measure r.r
+            v[0] = fused_update_only<COH>(st, alpha);
+        } else {
+            double ex[3];
+            v[1] = (pass == 0) ? strip_pass<MODE_FUSED0, SF, COH>(st, lc, 0.f, 0.f, ex)
+                               : strip_pass<MODE_FUSED, SF, COH>(st, lc, beta, alpha, ex);
+            v[0] = ex[0]; v[2] = ex[1]; v[3] = ex[2];
+        }
+        grid_allreduce4<WORLD>(a, v, pass & 1, gen, wsm, s_tot);
         const double S0 = v[0], S1 = v[1], S3 = v[3];
         if (!((float)S0 > tol2)) {                   // void pass, see cg_fused_kernel
             r1 = S0;
             alpha = 0.f;
             break;
         }
+        if (deferred) {
+            beta = (float)S0 / (float)r0;                                         // devicecalls.cu:262, r.r measured
+            r1 = S0;
+            alpha = 0.f;
+            deferred = false;
+            n_defer++;
+            continue;
+        }
         const double S2 = S1 - (double)beta * v[2];
         const float al = (float)S0 / (float)S1;                                   // devicecalls.cu:269
         const double rr = S0 - 2.0 * (double)al * S2 + (double)al * (double)al * S3;
+        deferred = !(rr > FUSED_DEFER_REL * S0);
         r0 = S0; r1 = rr;
-        beta = (float)rr / (float)S0;                                             // devicecalls.cu:262
+        beta = deferred ? 0.f : (float)rr / (float)S0;                            // devicecalls.cu:262
         alpha = al;
         k++;
         plane = (pass + 1) & 1;
@@ -980,7 +1091,7 @@ __global__ void __launch_bounds__(SW_NT, SRPS_FUSED_MINB) cg_persistent_fused_ke
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        sc->r1 = r1; sc->r0 = r0; sc->k = k; sc->beta = beta; sc->alpha = 0.f;
+        sc->r1 = r1; sc->r0 = r0; sc->k = k; sc->beta = beta; sc->alpha = 0.f; sc->defer = 0; sc->n_defer = n_defer;
         sc->active = 0;
     }
 }

@@ -68,7 +68,7 @@ template <int NT>
 __device__ __forceinline__ void peer_allreduce(const PeerComm& c, double* vals, int n) {
     if (c.world <= 1) { __syncthreads(); return; }
     __shared__ unsigned long long s_seq;
-    if (threadIdx.x == 0) s_seq = *c.seq + 1ull;
+    if (threadIdx.x == 0) s_seq = __ldcg(c.seq) + 1ull;
     __syncthreads();
     const unsigned long long seq = s_seq;
     const int slot = (int)(seq & (MB_SLOTS - 1));
@@ -100,12 +100,17 @@ __device__ __forceinline__ void peer_allreduce(const PeerComm& c, double* vals, 
 // fence + flag round trip); 8-byte stores are single transactions.  st.release / ld.acquire at system scope
 // keep "word seen" => "the sender's earlier halo stores are visible".  Called by all threads of the last block;
 // returns the rank-ordered world total to every thread.
+// `release` = the ranks exchange PLANE data around this reduction (ghost lines pushed into, or pulled out of, a
+// neighbour's planes): the words then form a system-scope release/acquire chain -- the writer blocks fenced their
+// stores (device scope) before taking their reduction ticket, the last block observed every ticket, fences at SYSTEM
+// scope (cumulative) and stores the word; the receiver polls the word and fences at system scope before anything
+// that reads the planes.  Pure scalar exchanges (release = false) need neither fence.
 template <int NT>
 __device__ __forceinline__ double peer_allreduce_scalar(const PeerComm& c, double v, bool release) {
     if (c.world <= 1) return v;
     __shared__ double s_part[MAX_RANKS];
     __shared__ unsigned long long s_seq1;
-    if (threadIdx.x == 0) { s_seq1 = *c.seq + 1ull; s_part[0] = v; }
+    if (threadIdx.x == 0) { s_seq1 = __ldcg(c.seq) + 1ull; s_part[0] = v; }
     __syncthreads();
     const unsigned long long seq = s_seq1;
     const unsigned long long tag = (seq & 0xffffffffull) << 32;
@@ -125,8 +130,11 @@ __device__ __forceinline__ double peer_allreduce_scalar(const PeerComm& c, doubl
         do { w0 = ld_relaxed_sys_u64(&c.local->ll[slot][t][0]); } while ((w0 & 0xffffffff00000000ull) != tag);
         do { w1 = ld_relaxed_sys_u64(&c.local->ll[slot][t][1]); } while ((w1 & 0xffffffff00000000ull) != tag);
         s_part[t] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+        // acquire side of the chain: "word of rank t seen" + this fence => rank t's plane stores that preceded its
+        // release fence are visible to everything ordered after the barrier below (the next pass / the next kernel)
+        if (release) __threadfence_system();
     }
-    __syncthreads();        // ghost lines are read by the NEXT kernel: the kernel boundary is the acquire
+    __syncthreads();
     double total = 0.0;
     for (int r = 0; r < c.world; r++) total += s_part[r];      // rank order: identical bits on every rank
     if (threadIdx.x == 0) *c.seq = seq;
@@ -142,7 +150,7 @@ __device__ __forceinline__ void peer_allreduce_small(const PeerComm& c, double* 
     __shared__ double s_part[MAX_RANKS][NV];
     __shared__ unsigned s_lo[MAX_RANKS][NV];
     __shared__ unsigned long long s_seqn;
-    if (threadIdx.x == 0) s_seqn = *c.seq + 1ull;
+    if (threadIdx.x == 0) s_seqn = __ldcg(c.seq) + 1ull;   // L2: the previous caller may have been another block
     __syncthreads();
     const unsigned long long seq = s_seqn;
     const unsigned long long tag = (seq & 0xffffffffull) << 32;
@@ -158,6 +166,7 @@ __device__ __forceinline__ void peer_allreduce_small(const PeerComm& c, double* 
         do { v = ld_relaxed_sys_u64(&c.local->ll[slot][t][w]); } while ((v & 0xffffffff00000000ull) != tag);
         got = (unsigned)(v & 0xffffffffull);
         if (!(w & 1)) s_lo[t][w >> 1] = got;
+        if (release) __threadfence_system();      // acquire side, see peer_allreduce_scalar
     }
     __syncthreads();
     if (talker && (w & 1))
@@ -181,7 +190,10 @@ __device__ __forceinline__ bool grid_reduce_last_world(double v, double* partial
     // block_pushed: THIS block stored halo lines into peer memory (system fence before its ticket);
     // kernel_pushes: some block of this kernel did (the last block releases at system scope before the mailbox words)
     if (!grid_reduce_last<NT>(v, partials, ticket, red_smem, total, block_pushed)) return false;
-    total = peer_allreduce_scalar<NT>(c, total, kernel_pushes);
+    // world > 1: every reduction is also the ordering point for the planes this kernel wrote (the neighbours PULL their
+    // ghost lines of r / y out of them in the next kernel), so the words always form a release/acquire chain
+    (void)kernel_pushes;
+    total = peer_allreduce_scalar<NT>(c, total, c.world > 1);
     return true;
 }
 

@@ -50,7 +50,10 @@ struct CgScalars {
     int max_iter;
     float tol2;
     int plane;        // fused CG: the ping-pong plane that holds the search direction of the pending z step
-    int pad_;
+    int defer;        // fused CG: the expanded |r_{k+1}|^2 cancelled (< 1e-6 r.r): the next pass only applies the pending
+                      // step and MEASURES r.r, beta comes from the measurement (see cg_fused_kernel)
+    int profile;      // srps_profile_kernels: keep the scalars as set by the host (timing of one pass in isolation)
+    int n_defer;      // deferred passes of this solve (diagnostics: srps_timings.cg_deferred)
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -70,6 +73,15 @@ __device__ __forceinline__ float4 ld4_sys(const float* p) {
     asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
     return r;
+}
+// loads of planes that are REWRITTEN inside the running kernel (single-launch persistent CG): 0 = never (one launch per
+// pass: read-only path), 1 = by this GPU only (plain load, ordered by the grid barrier's acquire), 2 = possibly by a peer
+// GPU (ghost lines read in place over NVLink: system scope, never served from this SM's L1)
+template <int COH>
+__device__ __forceinline__ float4 ld4_coh(const float* p) {
+    if (COH == 0) return ldg4(p);
+    if (COH == 1) return ld4(p);
+    return ld4_sys(p);
 }
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float f4get(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }

@@ -59,3 +59,19 @@ def test_blob_exchange_is_rank_ordered_gloo():
         p.join(timeout=60)
     for rank, blobs in res:
         assert blobs == [bytes([0]) * 16, bytes([1]) * 16]
+
+
+def test_synthetic_strips_are_slices_of_the_whole_scene():
+    """bench.py's scene generator: a strip of a scene holds exactly the values the whole scene has on those columns
+    (counter-based noise, apron for the z initialisation), so every GPU count solves the same scene."""
+    from srmeetsps_cuda_b200.synth import hash_normal, synth_scene_torch
+    import torch
+    x = hash_normal(torch.arange(0, 400000, dtype=torch.int64), 2000, 3)
+    assert abs(float(x.mean())) < 5e-3 and abs(float(x.std()) - 1.0) < 5e-3
+    h, w, sf, n = 64, 96, 4, 5
+    full = synth_scene_torch(h, w, sf, n, 2000, device="cpu", pin=False)
+    for world in (2, 3, 8):
+        parts = [synth_scene_torch(h, w, sf, n, 2000, device="cpu", pin=False, j0=j0, j1=j1) for j0, j1 in strip_bounds(w, world)]
+        assert np.array_equal(np.concatenate([p["z"] for p in parts]), full["z"])
+        assert np.array_equal(np.concatenate([p["z0s"] for p in parts]), full["z0s"])
+        assert np.array_equal(np.concatenate([p["I"] for p in parts], axis=2), full["I"])

@@ -143,3 +143,29 @@ def test_fused_cg_recurrence_is_the_reference_cg(cfg):
     assert k_fus == k_ref
     assert rel_rmse(z_fus, z_ref) <= 5e-7
     assert rel_rmse(z_fus, z_ref) <= 2.0 * rel_rmse(z_f64.astype(np.float32), z_ref) + 1e-9
+
+
+def test_fused_cg_guard_measures_when_the_expansion_cancels():
+    """Early convergence (a well-conditioned SPD system: every step removes most of the residual, the last ones almost
+    all of it): the expanded |r - alpha y|^2 of the fused recurrence cancels, the guard defers to a measured r.r and
+    the pass count / solution stay those of the reference's CG.  Without the guard beta is noise (or negative)."""
+    rng = np.random.default_rng(0)
+    n = 400
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    # clustered spectrum: CG needs about one pass per cluster; the residual collapses by > 1e3 per pass at the end
+    lam = np.concatenate([np.full(n - 3, 1.0), [2.0, 3.0, 5.0]])
+    A = ((Q * lam) @ Q.T).astype(np.float32)
+    A = 0.5 * (A + A.T)
+    mv = lambda v: (A @ v.astype(np.float32)).astype(np.float32)
+    x0 = np.zeros(n, np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    z_ref, k_ref = o.cg_reference(mv, x0, b, np.float32)
+    stats = {}
+    z_fus, k_fus = o.cg_fused_reference(mv, x0, b, np.float32, stats=stats)
+    assert stats["deferred"] >= 1, "the scenario must exercise the guard"
+    assert abs(k_fus - k_ref) <= 1
+    assert np.all(np.isfinite(z_fus))
+    sol = np.linalg.solve(A.astype(np.float64), b.astype(np.float64))
+    err_ref = np.linalg.norm(z_ref - sol) / np.linalg.norm(sol)
+    err_fus = np.linalg.norm(z_fus - sol) / np.linalg.norm(sol)
+    assert err_fus <= 2.0 * err_ref + 1e-6
