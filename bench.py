@@ -37,6 +37,7 @@ WORKLOADS = {
     "1080p": (1080, 1920, 4, 20, 1000),      # config 3
     "1k": (1024, 1024, 4, 32, 2000),         # the largest square both arms can run: the same-size pair of the reference ratio
     "small": (512, 512, 4, 8, 7),            # CI-sized
+    "n8sim": (4096, 1024, 4, 32, 2000),      # at 2 GPUs: the per-GPU strip of config 4 at 8 GPUs (512 lines x 4096 pixels)
 }
 PARITY_SCENE = (1024, 1024, 4, 8, 77, 3)     # strip_parity: h, w, sf, n, seed, outer iterations
 METRIC = "ms per outer iteration (4096x4096 HR, sf=4, 32 images)"
@@ -358,8 +359,9 @@ def time_workload(name, local, albedo, steps, warmup):
         for _ in range(warmup):
             ctx.outer_iteration()
         per, cg = [], []
+        cg_k = 0
         for _ in range(steps):
-            _, k = ctx.outer_iteration()
+            _, cg_k = ctx.outer_iteration()
             t = ctx.timings()
             per.append(t["ms_total"]); cg.append(t["ms_depth_cg"])
         out = {k: torch.empty(s_, dtype=torch.float32, pin_memory=True).numpy() for k, s_ in
@@ -374,7 +376,7 @@ def time_workload(name, local, albedo, steps, warmup):
     torch.cuda.empty_cache()
     return {"workload": f"{h}x{w} HR, sf={sf}, {n} images, full mask", "value": float(np.mean(per)), "unit": "ms",
             "min": float(np.min(per)), "median": float(np.median(per)), "e2e": float(e2e), "steps": steps, "warmup": warmup,
-            "ms_depth_cg": float(np.mean(cg)), "cg_iters": int(k)}
+            "ms_depth_cg": float(np.mean(cg)), "cg_iters": int(cg_k)}
 
 
 # ------------------------------------------------------------------------------------------------

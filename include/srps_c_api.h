@@ -94,8 +94,12 @@ int  srps_npixs(const srps_ctx* ctx);                /* imasks.size()  SRPS.cu:1
  * s=(0,0,-1,0), rho=0.5 and the first normals exactly as SRPS.cu:209-270.  I may be NULL if
  * srps_upload_images_u8 is used instead. */
 int  srps_upload_state(srps_ctx* ctx, const float* I, const float* z, const float* z0s);
-/* Same stack as 8-bit samples (I = v/255, the image loader's arithmetic, Utilities.cpp:343). */
+/* Same stack as 8-bit samples (I = v/255, the image loader's arithmetic, Utilities.cpp:343).  The samples STAY 8-bit
+ * in device memory (a quarter of the stack bytes per pass and per upload); the two stack passes divide by 255 in
+ * registers, bit-identical to uploading the floats v/255.f.  The _strided form reads a strip's run out of the planes
+ * of a global stack (see srps_upload_state_strided). */
 int  srps_upload_images_u8(srps_ctx* ctx, const unsigned char* I8);
+int  srps_upload_images_u8_strided(srps_ctx* ctx, const unsigned char* I8, long long plane_stride);
 /* Overwrite one state buffer from host (tests / resume).  After SRPS_BUF_Z call srps_normals. */
 int  srps_set_state(srps_ctx* ctx, int which, const float* host);
 int  srps_download(srps_ctx* ctx, int which, float* host);

@@ -37,6 +37,7 @@ EXPORTS = {
     "srps_npixs": (C.c_int, [C.c_void_p]),
     "srps_upload_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "srps_upload_images_u8": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "srps_upload_images_u8_strided": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong]),
     "srps_set_state": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "srps_download": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "srps_lighting": (C.c_int, [C.c_void_p]),

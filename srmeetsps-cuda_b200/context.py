@@ -103,9 +103,16 @@ class Context:
                  "srps_upload_state")
 
     def upload_images_u8(self, I8):
+        """The stack as 8-bit samples (kept 8-bit on the device; I = v/255 is formed in registers)."""
         I8 = np.ascontiguousarray(I8, dtype=np.uint8)
         assert I8.shape == (self.n, self.c, self.npix)
         self._ck(self.lib.srps_upload_images_u8(self._ctx, _ptr(I8)), "srps_upload_images_u8")
+
+    def upload_images_u8_strided(self, I8_first, plane_stride):
+        """Strip contexts: I8_first is a 1-D uint8 view starting at this strip's first pixel of plane 0 of the global stack."""
+        assert I8_first.dtype == np.uint8
+        self._ck(self.lib.srps_upload_images_u8_strided(self._ctx, _ptr(I8_first), int(plane_stride)),
+                 "srps_upload_images_u8_strided")
 
     _SHAPES = {L.BUF_S: lambda s: (s.n, s.c, 4), L.BUF_RHO: lambda s: (s.c, s.npix), L.BUF_Z: lambda s: (s.npix,),
                L.BUF_N: lambda s: (4, s.npix), L.BUF_DZ: lambda s: (s.npix,), L.BUF_Z0S: lambda s: (s.npixs,),

@@ -44,7 +44,11 @@ struct srps_ctx {
     unsigned char* types_base = nullptr; unsigned char* types = nullptr;
     unsigned char* lrmask = nullptr;
     int* idx = nullptr; int* idx_lr = nullptr;
+    // image stack: ONE of the two allocations is live (lazily, on the first upload): fp32 intensities, or the 8-bit
+    // samples of an image dataset kept 8-bit in HBM (srps_upload_images_u8; converted in registers by the stack passes)
     float* I = nullptr; float* I_base = nullptr;
+    unsigned char* I8 = nullptr; unsigned char* I8_base = nullptr;
+    bool stack_u8 = false;
     float *z = nullptr, *r = nullptr, *p = nullptr, *p2 = nullptr, *y = nullptr, *e0 = nullptr, *dz = nullptr, *dz_new = nullptr;
     float *r2 = nullptr, *y2 = nullptr;     // second residual / A p planes of the fused CG pass (ping-pong)
     float *w[3]{}, *gq[3]{}, *N[3]{}, *N_new[3]{}, *rho[3]{};
@@ -153,7 +157,7 @@ extern "C" void srps_ctx_destroy(srps_ctx* ctx) {
     }
     cudaFree(ctx->mailbox); cudaFree(ctx->seq); cudaFree(ctx->sync_words);
     cudaFree(ctx->plane_base); cudaFree(ctx->types_base); cudaFree(ctx->lrmask); cudaFree(ctx->idx); cudaFree(ctx->idx_lr);
-    cudaFree(ctx->I_base); cudaFree(ctx->z0lr); cudaFree(ctx->s); cudaFree(ctx->gram); cudaFree(ctx->lc); cudaFree(ctx->sc);
+    cudaFree(ctx->I_base); cudaFree(ctx->I8_base); cudaFree(ctx->z0lr); cudaFree(ctx->s); cudaFree(ctx->gram); cudaFree(ctx->lc); cudaFree(ctx->sc);
     cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->energy); cudaFree(ctx->staging); cudaFree(ctx->U);
     cudaFreeHost(ctx->h_energy); cudaFreeHost(ctx->h_sc);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -309,10 +313,7 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         CK(cudaMalloc(&ctx->U, sizeof(float) * (size_t)(15 * g.plane)));
         CK(cudaMemsetAsync(ctx->U, 0, sizeof(float) * (size_t)(15 * g.plane), ctx->stream));
     }
-    const size_t stack_floats = (size_t)ctx->n * 3 * (size_t)g.plane;
-    CK(cudaMalloc(&ctx->I_base, sizeof(float) * stack_floats));
-    CK(cudaMemsetAsync(ctx->I_base, 0, sizeof(float) * stack_floats, ctx->stream));
-    ctx->I = ctx->I_base + g.origin();
+    // (the image stack is allocated by the first upload: fp32 or 8-bit, see ensure_stack)
     CK(cudaMalloc(&ctx->types_base, (size_t)g.plane));
     CK(cudaMemcpyAsync(ctx->types_base, types.data(), (size_t)g.plane, cudaMemcpyHostToDevice, ctx->stream));
     ctx->types = ctx->types_base + g.origin();
@@ -404,9 +405,9 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_update_kernel, CG_NT, 0));
     ctx->grid_update = (int)std::min<long long>((ctx->n4 + CG_NT - 1) / CG_NT, (long long)ctx->sm_count * std::max(1, occ));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stack_project_kernel<true>, ST_NT, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (stack_project_kernel<true, float>), ST_NT, 0));
     ctx->grid_stack = (int)std::min<long long>((ctx->n4 + ST_NT - 1) / ST_NT, (long long)ctx->sm_count * std::max(1, occ));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lighting_reduce_kernel, ST_NT, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lighting_reduce_kernel<float>, ST_NT, 0));
     ctx->light_groups = (ctx->n + LIGHT_IB - 1) / LIGHT_IB;
     ctx->grid_light_x = (int)std::min<long long>((ctx->n4 + ST_NT - 1) / ST_NT,
                                                  std::max(1, ctx->sm_count * std::max(1, occ) / ctx->light_groups));
@@ -496,22 +497,59 @@ static int launch_normals(srps_ctx* ctx, bool energy, float* const* Nout, float*
     return 0;
 }
 
+// The stack in the requested sample type; switching type frees the other allocation (a context holds one stack).
+static int ensure_stack(srps_ctx* ctx, bool u8) {
+    const Grid& g = ctx->g;
+    const size_t samples = (size_t)ctx->n * 3 * (size_t)g.plane;
+    if (u8) {
+        if (ctx->I_base) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(ctx->I_base)); ctx->I_base = nullptr; ctx->I = nullptr; }
+        if (!ctx->I8_base) {
+            CK(cudaMalloc(&ctx->I8_base, samples));
+            CK(cudaMemsetAsync(ctx->I8_base, 0, samples, ctx->stream));
+            ctx->I8 = ctx->I8_base + g.origin();
+        }
+    } else {
+        if (ctx->I8_base) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(ctx->I8_base)); ctx->I8_base = nullptr; ctx->I8 = nullptr; }
+        if (!ctx->I_base) {
+            CK(cudaMalloc(&ctx->I_base, sizeof(float) * samples));
+            CK(cudaMemsetAsync(ctx->I_base, 0, sizeof(float) * samples, ctx->stream));
+            ctx->I = ctx->I_base + g.origin();
+        }
+    }
+    ctx->stack_u8 = u8;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 extern "C" int srps_upload_images_u8(srps_ctx* ctx, const unsigned char* I8) {
+    return srps_upload_images_u8_strided(ctx, I8, ctx ? ctx->npix : 0);
+}
+
+extern "C" int srps_upload_images_u8_strided(srps_ctx* ctx, const unsigned char* I8, long long plane_stride) {
     if (!ctx || !I8) return fail(ctx, SRPS_E_INVALID, "null argument");
+    if (plane_stride < ctx->npix) return fail(ctx, SRPS_E_INVALID, "plane_stride smaller than the pixel count");
     CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_stack(ctx, true))) return rc;
     const Grid& g = ctx->g;
     const int planes = ctx->n * 3;
-    const size_t per = (size_t)ctx->npix;
-    const int chunk = (int)std::max<size_t>(1, std::min<size_t>(planes, ctx->staging_bytes / per));
-    for (int p0 = 0; p0 < planes; p0 += chunk) {
-        const int np = std::min(chunk, planes - p0);
-        CK(cudaMemcpyAsync(ctx->staging, I8 + (size_t)p0 * per, per * np, cudaMemcpyHostToDevice, ctx->stream));
-        for (int k = 0; k < np; k++)
-            LAUNCH(ctx, scatter_u8_kernel, (ctx->npix + 255) / 256, 256, (const unsigned char*)ctx->staging + (size_t)k * per,
-                   ctx->idx, ctx->I + (long long)(p0 + k) * g.plane, ctx->npix);
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->full_rect) {
+        for (int pl = 0; pl < planes; pl++)
+            CK(cudaMemcpy2DAsync(ctx->I8 + (long long)pl * g.plane, (size_t)g.pitch, I8 + (size_t)pl * plane_stride, (size_t)g.nx,
+                                 (size_t)g.nx, g.ny, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        const size_t per = (size_t)ctx->npix;
+        const int chunk = (int)std::max<size_t>(1, std::min<size_t>(planes, ctx->staging_bytes / per));
+        for (int p0 = 0; p0 < planes; p0 += chunk) {
+            const int np = std::min(chunk, planes - p0);
+            CK(cudaMemcpy2DAsync(ctx->staging, per, I8 + (size_t)p0 * plane_stride, (size_t)plane_stride, per, np,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+            for (int k = 0; k < np; k++)
+                LAUNCH(ctx, scatter_u8_kernel, (ctx->npix + 255) / 256, 256, (const unsigned char*)ctx->staging + (size_t)k * per,
+                       ctx->idx, ctx->I8 + (long long)(p0 + k) * g.plane, ctx->npix);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
     }
     ctx->have_images = true;
     return 0;
@@ -527,6 +565,8 @@ extern "C" int srps_upload_state_strided(srps_ctx* ctx, const float* I, long lon
     CK(cudaSetDevice(ctx->device));
     const Grid& g = ctx->g;
     if (I) {
+        int rcs;
+        if ((rcs = ensure_stack(ctx, false))) return rcs;
         const int planes = ctx->n * 3;
         if (ctx->full_rect) {
             for (int pl = 0; pl < planes; pl++)
@@ -663,10 +703,11 @@ extern "C" int srps_lighting(srps_ctx* ctx) {
     ga.n4 = la.n4 = ctx->n4;
     ga.partials = ctx->partials; ga.ticket = ctx->tickets + 1; ga.gram = ctx->gram; ga.comm = ctx->comm; la.comm = ctx->comm;
     LAUNCH(ctx, lighting_gram_kernel, ctx->grid_gram, ST_NT, ga);
-    la.I = ctx->I; la.plane = ctx->g.plane; la.n_images = ctx->n;
+    la.I = ctx->stack_u8 ? (const void*)ctx->I8 : (const void*)ctx->I; la.plane = ctx->g.plane; la.n_images = ctx->n;
     la.partials = ctx->partials; la.ticket = ctx->tickets + 2; la.gram = ctx->gram; la.s = ctx->s; la.lc = ctx->lc;
     la.max_iter = ctx->h_sc[0].max_iter; la.tol2 = ctx->h_sc[0].tol2;
-    LAUNCH(ctx, lighting_reduce_kernel, dim3(ctx->grid_light_x, ctx->light_groups), ST_NT, la);
+    if (ctx->stack_u8) LAUNCH(ctx, lighting_reduce_kernel<unsigned char>, dim3(ctx->grid_light_x, ctx->light_groups), ST_NT, la);
+    else LAUNCH(ctx, lighting_reduce_kernel<float>, dim3(ctx->grid_light_x, ctx->light_groups), ST_NT, la);
     CK(cudaGetLastError());
     ctx->coeffs_valid = false;
     return publish_lc(ctx);
@@ -678,17 +719,19 @@ extern "C" int srps_albedo(srps_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     const bool refcg = ctx->prob.albedo_mode == SRPS_ALBEDO_REFERENCE_CG;
     ProjectArgs pa{};
-    pa.g = ctx->g; pa.I = ctx->I; pa.plane = ctx->g.plane; pa.n_images = ctx->n; pa.s = ctx->s; pa.lc = ctx->lc;
+    pa.g = ctx->g; pa.I = ctx->stack_u8 ? (const void*)ctx->I8 : (const void*)ctx->I; pa.plane = ctx->g.plane; pa.n_images = ctx->n; pa.s = ctx->s; pa.lc = ctx->lc;
     pa.types = ctx->types; pa.dz = ctx->dz; pa.e0 = ctx->e0; pa.U = ctx->U; pa.plane_u = ctx->g.plane; pa.n4 = ctx->n4;
     for (int c = 0; c < 3; c++) { pa.N[c] = ctx->N[c]; pa.rho[c] = ctx->rho[c]; pa.w[c] = ctx->w[c]; pa.gq[c] = ctx->gq[c]; }
     if (!refcg) {
-        LAUNCH(ctx, stack_project_kernel<true>, ctx->grid_stack, ST_NT, pa);
+        if (ctx->stack_u8) LAUNCH(ctx, (stack_project_kernel<true, unsigned char>), ctx->grid_stack, ST_NT, pa);
+        else LAUNCH(ctx, (stack_project_kernel<true, float>), ctx->grid_stack, ST_NT, pa);
         CK(cudaGetLastError());
         ctx->coeffs_valid = true;
         return 0;
     }
     pa.U = ctx->U + ctx->g.origin();
-    LAUNCH(ctx, stack_project_kernel<false>, ctx->grid_stack, ST_NT, pa);
+    if (ctx->stack_u8) LAUNCH(ctx, (stack_project_kernel<false, unsigned char>), ctx->grid_stack, ST_NT, pa);
+    else LAUNCH(ctx, (stack_project_kernel<false, float>), ctx->grid_stack, ST_NT, pa);
     AlbedoArgs aa{};
     aa.lc = ctx->lc; aa.U = pa.U; aa.plane_u = ctx->g.plane; aa.n4 = ctx->n4;
     for (int c = 0; c < 3; c++) { aa.N[c] = ctx->N[c]; aa.rho[c] = ctx->rho[c]; aa.d[c] = ctx->ad[c]; aa.r[c] = ctx->ar[c]; aa.p[c] = ctx->ap[c]; }

@@ -145,10 +145,11 @@ __global__ void scatter_kernel(const float* __restrict__ src, const int* __restr
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[idx[i]] = src[i];
 }
+// 8-bit samples stay 8-bit in HBM (the /255 of Utilities.cpp:343 happens in registers, srps_stack.cuh: u8_to_unit)
 __global__ void scatter_u8_kernel(const unsigned char* __restrict__ src, const int* __restrict__ idx,
-                                  float* __restrict__ dst, int n) {
+                                  unsigned char* __restrict__ dst, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[idx[i]] = (float)src[i] / 255.f;          // Utilities.cpp:343
+    if (i < n) dst[idx[i]] = src[i];
 }
 __global__ void gather_kernel(const float* __restrict__ src, const int* __restrict__ idx, float* __restrict__ dst, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

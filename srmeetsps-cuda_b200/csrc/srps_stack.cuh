@@ -23,6 +23,28 @@ constexpr int LIGHT_IB = SRPS_LIGHT_IB;    // images per CTA row in the lighting
 constexpr int MAX_IMAGES = 64; // n_images limit (shared-memory copy of s)
 
 // ---------------------------------------------------------------------------------------------
+// Storage type of the image stack.  float: intensities in [0,1] as the reference holds them (SRPS.cu:223-232).
+// unsigned char: the 8-bit samples the image loader read (Utilities.cpp:343 divides them by 255 on the host); the
+// division happens in registers instead, 4x fewer stack bytes per pass and per upload.  v/255.f is reproduced exactly
+// (same bits as the float path) by one reciprocal multiply and one FMA correction step -- q = v*r; q += (v - 255 q) r,
+// r = fl(1/255) -- which is the correctly rounded quotient for every v in 0..255 (checked exhaustively in exact
+// arithmetic, and by test_u8_upload_equals_float_upload on the device): 3 FP instructions instead of an IEEE division.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float u8_to_unit(unsigned v) {
+    const float f = (float)v;
+    const float r = 1.f / 255.f;                    // folded at compile time
+    const float q = f * r;
+    return fmaf(fmaf(-255.f, q, f), r, q);
+}
+template <typename T> __device__ __forceinline__ float4 ld_stack4(const T* plane, long long i4);
+template <> __device__ __forceinline__ float4 ld_stack4<float>(const float* plane, long long i4) { return ld4_stream(plane + 4 * i4); }
+template <> __device__ __forceinline__ float4 ld_stack4<unsigned char>(const unsigned char* plane, long long i4) {
+    unsigned u;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(u) : "l"(plane + 4 * i4));
+    return make_float4(u8_to_unit(u & 0xffu), u8_to_unit((u >> 8) & 0xffu), u8_to_unit((u >> 16) & 0xffu), u8_to_unit(u >> 24));
+}
+
+// ---------------------------------------------------------------------------------------------
 // generic multi-value single-pass grid reduction (values as float per thread, partials as double)
 // Returns true in the last block; totals[0..NV) then valid in shared memory `tot`.
 // ---------------------------------------------------------------------------------------------
@@ -117,7 +139,7 @@ __global__ void __launch_bounds__(ST_NT, 4) lighting_gram_kernel(const GramArgs 
 // and the per-iteration lighting constants S3/S4.
 // ---------------------------------------------------------------------------------------------
 struct LightArgs {
-    const float* I;        // stack base (origin-offset), plane stride `plane`
+    const void* I;         // stack base (origin-offset; float or unsigned char samples), plane stride `plane` in samples
     long long plane;
     const float* rho[3];
     const float* N[3];
@@ -176,7 +198,9 @@ __device__ inline void light_consts_from_s(const float* s, int n, LightConsts* l
 #ifndef SRPS_LIGHT_MINB
 #define SRPS_LIGHT_MINB 3
 #endif
+template <typename T>
 __global__ void __launch_bounds__(ST_NT, SRPS_LIGHT_MINB) lighting_reduce_kernel(const LightArgs a) {
+    const T* const stack = static_cast<const T*>(a.I);
     __shared__ double tot[LIGHT_IB * 12];
     __shared__ float wsm[(ST_NT / 32) * LIGHT_IB * 12];
     const int group = blockIdx.y;
@@ -194,7 +218,7 @@ __global__ void __launch_bounds__(ST_NT, SRPS_LIGHT_MINB) lighting_reduce_kernel
             float4 v[LIGHT_IB];
 #pragma unroll
             for (int ii = 0; ii < LIGHT_IB; ii++)
-                v[ii] = (ii < nimg) ? ld4_stream(a.I + ((long long)(i0 + ii) * 3 + c) * a.plane + 4 * i) : f4zero();
+                v[ii] = (ii < nimg) ? ld_stack4<T>(stack + ((long long)(i0 + ii) * 3 + c) * a.plane, i) : f4zero();
             const float4 a0 = make_float4(r.x * n0.x, r.y * n0.y, r.z * n0.z, r.w * n0.w);
             const float4 a1 = make_float4(r.x * n1.x, r.y * n1.y, r.z * n1.z, r.w * n1.w);
             const float4 a2 = make_float4(r.x * n2.x, r.y * n2.y, r.z * n2.z, r.w * n2.w);
@@ -277,7 +301,7 @@ __device__ __forceinline__ void depth_coeffs_px(const LightConsts& lc, const flo
 // ---------------------------------------------------------------------------------------------
 struct ProjectArgs {
     Grid g;
-    const float* I; long long plane; int n_images;
+    const void* I; long long plane; int n_images;     // stack base (float or unsigned char samples), plane stride in samples
     const float* s;               // [n][3][4] (device)
     const LightConsts* lc;
     const unsigned char* types;
@@ -296,8 +320,9 @@ struct ProjectArgs {
 #define SRPS_PROJ_UNROLL 4       // images in flight per thread; measured at 4096^2 x 32 (round 1): 4 -> 1.18 ms, 2 -> 1.38 ms
 #endif
 constexpr int PROJ_UNROLL = SRPS_PROJ_UNROLL;
-template <bool FUSED>
+template <bool FUSED, typename T>
 __global__ void __launch_bounds__(ST_NT, SRPS_PROJ_MINB) stack_project_kernel(const ProjectArgs a) {
+    const T* const stack = static_cast<const T*>(a.I);
     __shared__ float4 s_sm[MAX_IMAGES * 3];
     for (int e = threadIdx.x; e < a.n_images * 3; e += ST_NT) s_sm[e] = *reinterpret_cast<const float4*>(a.s + 4 * e);
     __syncthreads();
@@ -313,12 +338,11 @@ __global__ void __launch_bounds__(ST_NT, SRPS_PROJ_MINB) stack_project_kernel(co
 #pragma unroll
             for (int k = 0; k < 4; k++) U[c][k] = f4zero();
         }
-        const float* base = a.I + 4 * i;
 #pragma unroll PROJ_UNROLL
         for (int j = 0; j < a.n_images; j++) {
             float4 v[3];
 #pragma unroll
-            for (int c = 0; c < 3; c++) v[c] = ld4_stream(base + ((long long)j * 3 + c) * a.plane);
+            for (int c = 0; c < 3; c++) v[c] = ld_stack4<T>(stack + ((long long)j * 3 + c) * a.plane, i);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 const float4 sv = s_sm[j * 3 + c];

@@ -251,6 +251,38 @@ def test_u8_upload_equals_float_upload(mitten_scene):
     a.close(); b.close()
 
 
+def test_u8_stack_is_bit_identical_to_float_stack_on_every_sample_value():
+    """The 8-bit stack (srps_upload_images_u8: samples stay 8-bit in HBM, v/255 formed in registers by a reciprocal
+    multiply + one FMA correction) against the float stack holding v/255.f, on a full-rectangle mask (2-D copy upload
+    path) with every value 0..255 present: lighting, albedo and depth must agree bit for bit."""
+    from srmeetsps_cuda_b200 import Context
+    h, w, sf, n = 64, 96, 4, 5
+    rng = np.random.default_rng(4)
+    sc = o.synth_scene(h, w, sf, n, seed=3, mask_kind="full")
+    I8 = np.clip(np.rint(sc["I"] * 255.0), 0, 255).astype(np.uint8)
+    I8.reshape(-1)[:256] = np.arange(256, dtype=np.uint8)            # every sample value occurs
+    I8.reshape(-1)[256:4096] = rng.integers(0, 256, 4096 - 256, dtype=np.uint8)
+    If = (I8.astype(np.float32) / np.float32(255.0)).astype(np.float32)
+    a = Context(sc["mask"], n, sf, sc["K"])
+    a.upload_images_u8(I8)
+    a.upload_state(None, sc["z"], sc["z0s"])
+    b = Context(sc["mask"], n, sf, sc["K"])
+    b.upload_state(If, sc["z"], sc["z0s"])
+    for it in range(2):
+        ea, ka = a.outer_iteration()
+        eb, kb = b.outer_iteration()
+        assert (ea, ka) == (eb, kb)
+        for name in ("s", "rho", "z", "N"):
+            assert np.array_equal(a.download(name), b.download(name)), (it, name)
+    # switching the same context back to a float stack works (one stack allocation is live at a time)
+    a.upload_state(If, sc["z"], sc["z0s"])
+    ea, _ = a.outer_iteration()
+    b.upload_state(If, sc["z"], sc["z0s"])
+    eb, _ = b.outer_iteration()
+    assert ea == eb
+    a.close(); b.close()
+
+
 def test_run_applies_reference_stop_rule():
     """srps_run: stop when E rises, rel. change < 5e-3 or iteration > 10 (SRPS.cu:298-301)."""
     sc = scene(SCENES[2])
