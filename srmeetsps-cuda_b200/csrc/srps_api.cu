@@ -19,6 +19,7 @@
 #include "../../include/srps_c_api.h"
 #include "srps_cg.cuh"
 #include "srps_epilogue.cuh"
+#include "srps_geom.cuh"
 #include "srps_stack.cuh"
 
 using namespace srps;
@@ -172,9 +173,14 @@ static const void* fn_strip_iter(int sf) {
     return sf == 1 ? (const void*)stencil_strip_kernel<MODE_ITER, 1> : (sf == 2 ? (const void*)stencil_strip_kernel<MODE_ITER, 2>
                                                                                 : (const void*)stencil_strip_kernel<MODE_ITER, 4>);
 }
-static const void* fn_fused(int sf, bool first) {
-    if (first) return sf == 1 ? (const void*)cg_fused_kernel<1, true> : (sf == 2 ? (const void*)cg_fused_kernel<2, true> : (const void*)cg_fused_kernel<4, true>);
-    return sf == 1 ? (const void*)cg_fused_kernel<1, false> : (sf == 2 ? (const void*)cg_fused_kernel<2, false> : (const void*)cg_fused_kernel<4, false>);
+template <bool FIRST, bool LLG>
+static const void* fn_fused_t(int sf) {
+    return sf == 1 ? (const void*)cg_fused_kernel<1, FIRST, LLG> : (sf == 2 ? (const void*)cg_fused_kernel<2, FIRST, LLG>
+                                                                            : (const void*)cg_fused_kernel<4, FIRST, LLG>);
+}
+static const void* fn_fused(int sf, bool first, bool world) {       // world: strip partition (LL ghost lines)
+    if (world) return first ? fn_fused_t<true, true>(sf) : fn_fused_t<false, true>(sf);
+    return first ? fn_fused_t<true, false>(sf) : fn_fused_t<false, false>(sf);
 }
 static const void* fn_persistent(int sf) {
     return sf == 1 ? (const void*)cg_persistent_kernel<1> : (sf == 2 ? (const void*)cg_persistent_kernel<2> : (const void*)cg_persistent_kernel<4>);
@@ -207,43 +213,39 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     const char* ug = getenv("SRPS_NO_GRAPH");
     ctx->use_graph = (ug && ug[0] == '1') ? 0 : 1;
 
-    // ---- geometry of the mask (host, one-shot): bounding box rounded out to sf
-    const unsigned char* m = prob->mask;
-    int imin = h, imax = -1, jmin = w, jmax = -1;
-    long long npix = 0;
-    for (int j = 0; j < w; j++)
-        for (int i = 0; i < h; i++)
-            if (m[(size_t)i + (size_t)j * h]) {
-                npix++;
-                imin = std::min(imin, i); imax = std::max(imax, i);
-                jmin = std::min(jmin, j); jmax = std::max(jmax, j);
-            }
-    if (npix == 0) return fail(ctx, SRPS_E_INVALID, "empty mask");
-    // (a strip without mask pixels is rejected below, once the owned columns are known)
+    // ---- geometry of the mask, analysed on the device (srps_geom.cuh): bounding box rounded out to sf, counts
+    unsigned char* d_mask = nullptr;
+    MaskStats* d_stats = nullptr;
+    struct Scratch {          // freed on every exit path of this function
+        unsigned char*& m; MaskStats*& s; unsigned* c = nullptr; unsigned long long* t = nullptr;
+        ~Scratch() { cudaFree(m); cudaFree(s); cudaFree(c); cudaFree(t); }
+    } scratch{d_mask, d_stats};
+    CK(cudaMalloc(&d_mask, (size_t)h * w));
+    CK(cudaMalloc(&d_stats, sizeof(MaskStats)));
+    CK(cudaMemcpyAsync(d_mask, prob->mask, (size_t)h * w, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->rank = 0; ctx->world = 1;
+    int j_lo = 0, j_hi = w;
+    if (prob->world > 1) { ctx->rank = prob->rank; ctx->world = prob->world; j_lo = prob->strip_j0; j_hi = prob->strip_j1; }
+    LAUNCH(ctx, mask_stats_init_kernel, 1, 1, d_stats, h, w);
+    LAUNCH(ctx, mask_stats_kernel, std::min(w, ctx->sm_count * 8), GEO_NT, d_mask, h, w, j_lo, j_hi, d_stats);
+    if (ctx->world > 1 && j_lo > 0)
+        LAUNCH(ctx, lr_count_before_kernel, ctx->sm_count * 4, GEO_NT, d_mask, h, w, sf, j_lo / sf, d_stats);
+    CK(cudaGetLastError());
+    MaskStats ms;
+    CK(cudaMemcpyAsync(&ms, d_stats, sizeof ms, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ms.total == 0) return fail(ctx, SRPS_E_INVALID, "empty mask");
+    long long npix = (long long)ms.total;
     Grid& g = ctx->g;
     g.sf = sf;
-    g.ib0 = imin / sf * sf; g.jb0 = jmin / sf * sf;
-    int ib1 = (imax + sf) / sf * sf, jb1 = (jmax + sf) / sf * sf;
-    ctx->rank = 0; ctx->world = 1;
-    if (prob->world > 1) {
+    g.ib0 = ms.imin / sf * sf; g.jb0 = ms.jmin / sf * sf;
+    int ib1 = (ms.imax + sf) / sf * sf, jb1 = (ms.jmax + sf) / sf * sf;
+    if (ctx->world > 1) {
         // strip partition: the pixel-row range stays the GLOBAL bounding range (same pitch on every rank),
         // the lines are exactly the owned image columns
-        ctx->rank = prob->rank; ctx->world = prob->world;
-        g.jb0 = prob->strip_j0; jb1 = prob->strip_j1;
-        npix = 0;
-        long long before = 0, lr_before = 0;
-        for (int j = 0; j < jb1; j++)
-            for (int i = 0; i < h; i++)
-                if (m[(size_t)i + (size_t)j * h]) { if (j < g.jb0) before++; else npix++; }
-        for (int q = 0; q < g.jb0 / sf; q++)
-            for (int r = 0; r < h / sf; r++) {
-                bool all = true;
-                for (int l = 0; l < sf && all; l++)
-                    for (int k = 0; k < sf; k++)
-                        if (!m[(size_t)(r * sf + k) + (size_t)(q * sf + l) * h]) { all = false; break; }
-                lr_before += all;
-            }
-        ctx->pix0 = before; ctx->lr0 = lr_before;
+        g.jb0 = j_lo; jb1 = j_hi;
+        npix = (long long)ms.inside;
+        ctx->pix0 = (long long)ms.before; ctx->lr0 = (long long)ms.lr_before;
         if (npix == 0) return fail(ctx, SRPS_E_INVALID, "this rank's strip holds no mask pixel (cut the strips over the mask's column range)");
     }
     g.nx = ib1 - g.ib0; g.ny = jb1 - g.jb0;
@@ -258,42 +260,40 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     ctx->tiles_y = (g.ny + TY - 1) / TY;
     ctx->full_rect = (npix == (long long)g.nx * g.ny);
 
-    std::vector<unsigned char> types((size_t)g.plane, 0);
-    std::vector<int> idx((size_t)std::max<long long>(npix, 1));
-    std::vector<unsigned char> lrmask((size_t)g.lny * g.lpitch, 0);
-    std::vector<int> idx_lr;
-    auto M = [&](int i, int j) -> bool { return i >= 0 && i < h && j >= 0 && j < w && m[(size_t)i + (size_t)j * h]; };
-    // LR mask: all sf*sf pixels inside (D*mask == 1, SRPS.cu:110-111); masked LR order = ascending r + q*(h/sf)
-    for (int bl = 0; bl < g.lny; bl++)
-        for (int bx = 0; bx < g.lnx; bx++) {
-            bool all = true;
-            for (int l = 0; l < sf && all; l++)
-                for (int k = 0; k < sf; k++)
-                    if (!M(g.ib0 + bx * sf + k, g.jb0 + bl * sf + l)) { all = false; break; }
-            if (all) { lrmask[(size_t)bl * g.lpitch + bx] = 1; idx_lr.push_back(bl * g.lpitch + bx); }
-        }
-    ctx->npixs = (int)idx_lr.size();
-    size_t pcount = 0;
-    const int ghost = ctx->world > 1 ? 1 : 0;          // ghost lines carry the neighbour strip's stencil types
-    for (int j = g.jb0 - ghost; j < jb1 + ghost && j < w; j++)
-        for (int i = g.ib0; i < ib1 && i < h; i++) {
-            if (j < 0 || !M(i, j)) continue;
-            if (j < g.jb0 || j >= jb1) {               // ghost line: types only
-                unsigned char t = T_MASK;
-                if (M(i, j + 1)) t |= T_XF; else if (M(i, j - 1)) t |= T_XB;
-                if (M(i + 1, j)) t |= T_YF; else if (M(i - 1, j)) t |= T_YB;
-                types[(size_t)(g.origin() + (long long)(j - g.jb0) * g.pitch + (i - g.ib0))] = t;
-                continue;
-            }
-            unsigned char t = T_MASK;
-            if (M(i, j + 1)) t |= T_XF; else if (M(i, j - 1)) t |= T_XB;        // SRPS.cu:39-46
-            if (M(i + 1, j)) t |= T_YF; else if (M(i - 1, j)) t |= T_YB;        // SRPS.cu:31-38
-            const int line = j - g.jb0, col = i - g.ib0;
-            if (lrmask[(size_t)(line / sf) * g.lpitch + col / sf]) t |= T_LR;
-            const long long off = (long long)line * g.pitch + col;
-            types[(size_t)(g.origin() + off)] = t;
-            idx[pcount++] = (int)off;
-        }
+    // LR mask (all sf*sf pixels inside: D*mask == 1, SRPS.cu:110-111), stencil types (make_gradient, SRPS.cu:23-71; ghost
+    // lines of a strip carry the neighbour strip's types) and the two index lists in the reference's masked orders
+    // (imask: ascending i + j*h = ascending dense offset; imasks: ascending r + q*(h/sf)), all on the device
+    const size_t lr_cells = (size_t)g.lny * g.lpitch;
+    CK(cudaMalloc(&ctx->types_base, (size_t)g.plane));
+    CK(cudaMemsetAsync(ctx->types_base, 0, (size_t)g.plane, ctx->stream));
+    ctx->types = ctx->types_base + g.origin();
+    CK(cudaMalloc(&ctx->lrmask, std::max<size_t>(lr_cells, 1)));
+    CK(cudaMemsetAsync(ctx->lrmask, 0, std::max<size_t>(lr_cells, 1), ctx->stream));
+    const int ghost = ctx->world > 1 ? 1 : 0;
+    const int geo_grid = ctx->sm_count * 8;
+    LAUNCH(ctx, lr_mask_kernel, geo_grid, GEO_NT, d_mask, h, w, g, ctx->lrmask);
+    LAUNCH(ctx, stencil_types_kernel, geo_grid, GEO_NT, d_mask, h, w, g, ghost, ctx->lrmask, ctx->types);
+    const int nlines = std::max(g.ny, g.lny);
+    CK(cudaMalloc(&scratch.c, sizeof(unsigned) * (size_t)(g.ny + std::max(g.lny, 1))));
+    CK(cudaMalloc(&scratch.t, sizeof(unsigned long long) * 2));
+    unsigned* cnt_hr = scratch.c; unsigned* cnt_lr = scratch.c + g.ny;
+    LAUNCH(ctx, line_count_kernel, std::min(g.ny, geo_grid), GEO_NT, ctx->types, g.pitch, g.nx, g.ny, T_MASK, cnt_hr);
+    LAUNCH(ctx, scan_counts_kernel, 1, 1024, cnt_hr, g.ny, scratch.t + 0);
+    LAUNCH(ctx, line_count_kernel, std::max(1, std::min(g.lny, geo_grid)), GEO_NT, ctx->lrmask, g.lpitch, g.lnx, g.lny, (unsigned char)1, cnt_lr);
+    LAUNCH(ctx, scan_counts_kernel, 1, 1024, cnt_lr, g.lny, scratch.t + 1);
+    CK(cudaGetLastError());
+    unsigned long long totals[2] = {0ull, 0ull};
+    CK(cudaMemcpyAsync(totals, scratch.t, sizeof totals, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    (void)nlines;
+    if ((long long)totals[0] != npix) return fail(ctx, SRPS_E_INVALID, "internal: device index count disagrees with the mask statistics");
+    ctx->npixs = (int)totals[1];
+    CK(cudaMalloc(&ctx->idx, sizeof(int) * (size_t)std::max<long long>(npix, 1)));
+    CK(cudaMalloc(&ctx->idx_lr, sizeof(int) * (size_t)std::max(ctx->npixs, 1)));
+    LAUNCH(ctx, line_fill_kernel, std::min(g.ny, geo_grid), GEO_NT, ctx->types, g.pitch, g.nx, g.ny, T_MASK, cnt_hr, ctx->idx);
+    if (ctx->npixs > 0)
+        LAUNCH(ctx, line_fill_kernel, std::min(g.lny, geo_grid), GEO_NT, ctx->lrmask, g.lpitch, g.lnx, g.lny, (unsigned char)1, cnt_lr, ctx->idx_lr);
+    CK(cudaGetLastError());
 
     // ---- device memory: one allocation for all per-pixel fp32 planes
     const bool refcg = prob->albedo_mode == SRPS_ALBEDO_REFERENCE_CG;
@@ -314,17 +314,8 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         CK(cudaMemsetAsync(ctx->U, 0, sizeof(float) * (size_t)(15 * g.plane), ctx->stream));
     }
     // (the image stack is allocated by the first upload: fp32 or 8-bit, see ensure_stack)
-    CK(cudaMalloc(&ctx->types_base, (size_t)g.plane));
-    CK(cudaMemcpyAsync(ctx->types_base, types.data(), (size_t)g.plane, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->types = ctx->types_base + g.origin();
-    CK(cudaMalloc(&ctx->lrmask, lrmask.size()));
-    CK(cudaMemcpyAsync(ctx->lrmask, lrmask.data(), lrmask.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMalloc(&ctx->idx, sizeof(int) * (size_t)npix));
-    CK(cudaMemcpyAsync(ctx->idx, idx.data(), sizeof(int) * (size_t)npix, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMalloc(&ctx->idx_lr, sizeof(int) * std::max<size_t>(1, idx_lr.size())));
-    if (!idx_lr.empty()) CK(cudaMemcpyAsync(ctx->idx_lr, idx_lr.data(), sizeof(int) * idx_lr.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMalloc(&ctx->z0lr, sizeof(float) * lrmask.size()));
-    CK(cudaMemsetAsync(ctx->z0lr, 0, sizeof(float) * lrmask.size(), ctx->stream));
+    CK(cudaMalloc(&ctx->z0lr, sizeof(float) * std::max<size_t>(lr_cells, 1)));
+    CK(cudaMemsetAsync(ctx->z0lr, 0, sizeof(float) * std::max<size_t>(lr_cells, 1), ctx->stream));
     CK(cudaMalloc(&ctx->s, sizeof(float) * (size_t)ctx->n * 12));
     CK(cudaMalloc(&ctx->gram, sizeof(float) * 48));
     static_assert(LC_SLOTS <= 64, "slot bitmap is one 64-bit word");
@@ -334,8 +325,10 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     CK(cudaMalloc(&ctx->sc, sizeof(CgScalars) * 4));
     CK(cudaMalloc(&ctx->tickets, sizeof(unsigned) * 8));
     CK(cudaMemsetAsync(ctx->tickets, 0, sizeof(unsigned) * 8, ctx->stream));
-    CK(cudaMalloc(&ctx->mailbox, sizeof(Mailbox)));
-    CK(cudaMemsetAsync(ctx->mailbox, 0, sizeof(Mailbox), ctx->stream));
+    // mailbox + (behind it, in the same IPC-exported allocation) the LL ghost-line buffer of the fused CG pass
+    static_assert(sizeof(Mailbox) % 16 == 0, "the LL ghost buffer behind the mailbox needs 16-byte alignment");
+    CK(cudaMalloc(&ctx->mailbox, sizeof(Mailbox) + ghost_ll_bytes(g.pitch)));
+    CK(cudaMemsetAsync(ctx->mailbox, 0, sizeof(Mailbox) + ghost_ll_bytes(g.pitch), ctx->stream));
     CK(cudaMalloc(&ctx->seq, sizeof(unsigned long long)));
     CK(cudaMemsetAsync(ctx->seq, 0, sizeof(unsigned long long), ctx->stream));
     ctx->comm.rank = 0; ctx->comm.world = 1; ctx->comm.local = ctx->mailbox; ctx->comm.seq = ctx->seq;
@@ -390,8 +383,8 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         // one strip geometry for all CG forms of this context: the occupancy of the instances that can be launched
         // (the <sf> instances, not a representative: a cooperative grid sized by another instance's occupancy could
         //  exceed what is resident at once)
-        occ = std::max(1, std::min({occupancy(fn_strip_iter(sfk), SW_NT), occupancy(fn_fused(sfk, false), SW_NT),
-                                    occupancy(fn_fused(sfk, true), SW_NT), ctx->use_persistent ? occ_p : 1 << 20}));
+        occ = std::max(1, std::min({occupancy(fn_strip_iter(sfk), SW_NT), occupancy(fn_fused(sfk, false, ctx->world > 1), SW_NT),
+                                    occupancy(fn_fused(sfk, true, ctx->world > 1), SW_NT), ctx->use_persistent ? occ_p : 1 << 20}));
         const int warps = ctx->sm_count * occ * (SW_NT / 32);
         int cl = (int)(((long long)g.ny * ctx->strip_n + warps - 1) / warps);
         cl = std::min(256, std::max(8, round_up(cl, SW_G)));
@@ -780,6 +773,13 @@ static void fill_stencil_args(srps_ctx* ctx, StencilArgs& sa) {
     peer_boundary_lines(ctx, ctx->r, sa.r_prev_line, sa.r_next_line);
     sa.y_in = nullptr; sa.r_out = nullptr; sa.x = nullptr; sa.y_prev_line = nullptr; sa.y_next_line = nullptr; sa.plane = 0;
     sa.lc_slot = ctx->lc_slot;
+    sa.ll = GhostLL{nullptr, nullptr, nullptr, ctx->g.pitch};
+    if (ctx->connected) {
+        auto ghost_of = [](Mailbox* mb) { return (unsigned long long*)((char*)mb + sizeof(Mailbox)); };
+        sa.ll.in = ghost_of(ctx->mailbox);
+        if (ctx->rank > 0) sa.ll.out_prev = ghost_of(ctx->comm.peer[ctx->rank - 1]);
+        if (ctx->rank + 1 < ctx->world) sa.ll.out_next = ghost_of(ctx->comm.peer[ctx->rank + 1]);
+    }
 }
 
 // Ghost-line addresses of plane `local_plane` inside the two neighbours' (mapped) plane allocations.
@@ -849,21 +849,18 @@ static void set_fused_pass(srps_ctx* ctx, StencilArgs& sa, int k) {
     sa.p_in = pp[k & 1]; sa.p_out = pp[(k + 1) & 1];
     sa.plane = (k + 1) & 1;
     sa.x = ctx->z;
-    peer_boundary_lines(ctx, sa.r, sa.r_prev_line, sa.r_next_line);
-    peer_boundary_lines(ctx, sa.y_in, sa.y_prev_line, sa.y_next_line);
+    // strip partition: the first pass of a solve pulls the ghost lines of r out of the neighbours' planes (the residual
+    // kernel wrote them and ordered them with its system-scope reduction); every later pass reads the LL words its
+    // neighbours pushed during the pass before (sa.ll) and pulls nothing
+    sa.r_prev_line = sa.r_next_line = sa.y_prev_line = sa.y_next_line = nullptr;
+    if (k == 0) peer_boundary_lines(ctx, sa.r, sa.r_prev_line, sa.r_next_line);
 }
 
-static void launch_fused_pass(srps_ctx* ctx, const StencilArgs& sa, bool first) {
-    const int sf = ctx->g.sf;
-    if (first) {
-        if (sf == 1) LAUNCH(ctx, (cg_fused_kernel<1, true>), ctx->grid_strip, SW_NT, sa);
-        else if (sf == 2) LAUNCH(ctx, (cg_fused_kernel<2, true>), ctx->grid_strip, SW_NT, sa);
-        else LAUNCH(ctx, (cg_fused_kernel<4, true>), ctx->grid_strip, SW_NT, sa);
-    } else {
-        if (sf == 1) LAUNCH(ctx, (cg_fused_kernel<1, false>), ctx->grid_strip, SW_NT, sa);
-        else if (sf == 2) LAUNCH(ctx, (cg_fused_kernel<2, false>), ctx->grid_strip, SW_NT, sa);
-        else LAUNCH(ctx, (cg_fused_kernel<4, false>), ctx->grid_strip, SW_NT, sa);
-    }
+static int launch_fused_pass(srps_ctx* ctx, const StencilArgs& sa, bool first) {
+    void* kargs[] = {(void*)&sa};
+    CK(cudaLaunchKernel(fn_fused(ctx->g.sf, first, ctx->world > 1), dim3(ctx->grid_strip), dim3(SW_NT), kargs, 0, ctx->stream));
+    ctx->launches++;
+    return 0;
 }
 
 static void launch_fused_tail(srps_ctx* ctx) {
@@ -1145,15 +1142,20 @@ extern "C" int srps_profile_kernels(srps_ctx* ctx, int reps, float* out_ms) {
     // fused pass alone (pending step alpha, beta as above; the last block rewrites the scalars: re-arm before each launch
     // is not needed for timing -- alpha/beta stay finite and the kernel stays active while k <= max_iter)
     out_ms[4] = 0.f;
+    int rc0 = 0;
     if (ctx->use_strip) {
         CK(cudaMemcpyAsync(ctx->sc, h, sizeof(CgScalars), cudaMemcpyHostToDevice, ctx->stream));
         StencilArgs sf_ = sa;
         for (int pass = 0; pass < 2; pass++) {
             if (pass == 1) CK(cudaEventRecord(e0, ctx->stream));
             for (int k = 0; k < (pass ? reps : 2); k++) {
-                set_fused_pass(ctx, sf_, k);     // launch 0 reads r, y, p of the last solve; then the planes alternate
+                // launch 0 reads r, y, p of the last solve; then the planes alternate.  Strip partition: the very first
+                // launch must be a FIRST pass (it pulls its ghost lines; a later pass waits for LL words that only a
+                // preceding fused pass pushes)
+                const bool first = (pass == 0 && k == 0);
+                set_fused_pass(ctx, sf_, first ? 0 : 2 + k);
                 sf_.x = ctx->dz_new;             // scratch plane: z itself is not touched
-                launch_fused_pass(ctx, sf_, false);
+                if ((rc0 = launch_fused_pass(ctx, sf_, first))) return rc0;
             }
         }
         CK(cudaEventRecord(e1, ctx->stream));

@@ -62,6 +62,7 @@ struct StencilArgs {
     const float* y_prev_line;              // previous rank's line ny_prev-1 of y_in
     const float* y_next_line;              // next rank's line 0 of y_in
     int plane;                             // which ping-pong plane p_out is (recorded for cg_tail_kernel)
+    GhostLL ll;                            // strip partition, fused pass: pushed ghost lines of r / y in LL format (srps_comm.cuh)
     int lc_slot;                           // warp-strip kernels: this context's slot of c_lc (constant-bank copy of *lc)
 };
 
@@ -377,9 +378,13 @@ __device__ __forceinline__ LineQ line_q(const LightConsts& lc, float fx, float f
 // are the ping-pong planes of this pass; returns this thread's partial of p.y (MODE_ITER).
 // COH: how planes that are rewritten between passes (r, y, p) are loaded -- 0: one launch per pass, read-only path;
 // 1 / 2: inside a single-launch persistent CG (ld4_coh, srps_common.cuh).  types and w never change during a solve.
-template <int MODE, int SF, int COH = 0>
+// LLG (fused pass of a strip partition): the boundary lines of r_out and y are PUSHED to the neighbours as LL words
+// tagged tag_in + 1, and -- MODE_FUSED -- the ghost lines of r and y_in are read from this rank's LL buffer (tag_in)
+// instead of being pulled from the neighbours' planes; MODE_FUSED0 (first pass of a solve) still pulls r, which the
+// residual kernel wrote and ordered with its system-scope reduction.
+template <int MODE, int SF, int COH = 0, bool LLG = false>
 __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightConsts& lc, float beta, float alpha = 0.f,
-                                             double* extra = nullptr /* FUSED: r.r, y_in.p, y.y */) {
+                                             double* extra = nullptr /* FUSED: r.r, y_in.p, y.y */, unsigned tag_in = 0u) {
     static_assert(MODE == MODE_ITER || MODE == MODE_APPLY || MODE == MODE_FUSED || MODE == MODE_FUSED0,
                   "the warp-strip kernel implements ITER, APPLY and the fused pass");
     constexpr bool FUSED = (MODE == MODE_FUSED || MODE == MODE_FUSED0);
@@ -446,6 +451,25 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
             ypn = (y4.x * pn.x + y4.y * pn.y) + (y4.z * pn.z + y4.w * pn.w);      // (A p_in).p : the conjugacy defect, see cg_fused_kernel
             return pn;
         };
+        // LLG: line -1 (side 0) / ny (side 1) of r and y_in out of this rank's LL ghost buffer; p_in is local
+        auto load_ghost = [&](int side, int j, float4& rn, float4& pin, float& ypn) -> float4 {
+            const bool ok = colok && x >= 0;
+            float4 r4 = f4zero(), y4 = f4zero();
+            if (ok) {
+                r4 = ll_load4(a.ll.in + a.ll.at(tag_in, side, 0), x, tag_in);
+                y4 = ll_load4(a.ll.in + a.ll.at(tag_in, side, 1), x, tag_in);
+            }
+            pin = ld4_coh<(COH ? 1 : 0)>(a.p_in + (ok ? (long long)j * pitch + x : 0));
+            rn = make_float4(r4.x - alpha * y4.x, r4.y - alpha * y4.y, r4.z - alpha * y4.z, r4.w - alpha * y4.w);
+            const float4 pn = make_float4(rn.x + beta * pin.x, rn.y + beta * pin.y, rn.z + beta * pin.z, rn.w + beta * pin.w);
+            ypn = (y4.x * pn.x + y4.y * pn.y) + (y4.z * pn.z + y4.w * pn.w);
+            return pn;
+        };
+        // LLG: this pass's boundary lines of array `arr` (0 = r_out, 1 = y) to the neighbours, for their next pass
+        auto push_boundary = [&](int j, int arr, const float4& v) {
+            if (j == 0 && a.ll.out_prev) ll_store4(a.ll.out_prev + a.ll.at(tag_in + 1u, 1, arr), x, v, tag_in + 1u);
+            if (j == ny - 1 && a.ll.out_next) ll_store4(a.ll.out_next + a.ll.at(tag_in + 1u, 0, arr), x, v, tag_in + 1u);
+        };
         // z is read and written by this kernel (each float4 by its owner only): coherent load, clamped like the others
         auto load_x = [&](int j) -> float4 {
             const bool ok = colok && j <= ny;
@@ -456,6 +480,7 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
             if (writer && j < jB) {
                 const long long off = (long long)j * pitch + x;
                 st4(a.r_out + off, rn);
+                if (LLG) push_boundary(j, 0, rn);
                 if (MODE == MODE_FUSED)
                     st4(a.x + off, make_float4(xo.x + alpha * pin.x, xo.y + alpha * pin.y, xo.z + alpha * pin.z, xo.w + alpha * pin.w));
                 s_rr += (double)((rn.x * rn.x + rn.y * rn.y) + (rn.z * rn.z + rn.w * rn.w));
@@ -479,7 +504,11 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
             float4 w0, w1, w2;
             float4 pin0 = f4zero(), x0 = f4zero(), r0 = f4zero();
             float yp0 = 0.f;
-            if (FUSED) { float4 rdum, pdum; float ydum; pprev = load_fused(jA - 1, rdum, pdum, ydum); } else pprev = load_pn(jA - 1);
+            if (FUSED) {
+                float4 rdum, pdum; float ydum;
+                if (LLG && MODE == MODE_FUSED && chunk == 0 && a.comm.rank > 0) pprev = load_ghost(0, -1, rdum, pdum, ydum);
+                else pprev = load_fused(jA - 1, rdum, pdum, ydum);
+            } else pprev = load_pn(jA - 1);
             const unsigned tp = load_t(jA - 1);
             load_w(jA - 1, w0, w1, w2);
             if (FUSED) { pl[0] = load_fused(jA, r0, pin0, yp0); if (MODE == MODE_FUSED) x0 = load_x(jA); } else pl[0] = load_pn(jA);
@@ -499,7 +528,10 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
 #pragma unroll
             for (int l = 1; l <= SW_G; l++) {
                 if (FUSED) {
-                    pl[l] = load_fused(j0 + l, rn[l], pin[l], ypn[l]);
+                    if (LLG && MODE == MODE_FUSED && l == SW_G && j0 + SW_G == ny && a.comm.rank + 1 < a.comm.world)
+                        pl[l] = load_ghost(1, ny, rn[l], pin[l], ypn[l]);        // the ghost line below the strip (warp-uniform branch)
+                    else
+                        pl[l] = load_fused(j0 + l, rn[l], pin[l], ypn[l]);
                     xo[l] = (MODE == MODE_FUSED) ? load_x(j0 + l) : f4zero();
                 } else {
                     pl[l] = load_pn(j0 + l);
@@ -563,6 +595,7 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
                 if (writer && j < jB) {
                     const long long off = (long long)j * pitch + x;
                     st4(a.y + off, out);
+                    if (LLG) push_boundary(j, 1, out);
                     if (KEEPS_P) { st4(a.p_out + off, pc); dot += (double)dl; }
                     if (FUSED) s_yy += (double)dyy;
                 }
@@ -720,8 +753,8 @@ constexpr int FUSED_SPARE_PASSES = 2;        // pass slots a solve has for defer
 // Deferred pass (see the header comment): r_out = r - alpha y ; z += alpha p ; p_out = p ; y_out = y ; returns this
 // thread's share of |r_out|^2.  Element-wise over the owned lines; p is copied on the two ghost / guard lines as well
 // (strip partition: the neighbours' p there is kept redundantly; r and y ghosts are pulled, not stored).
-template <int COH>
-__device__ __forceinline__ double fused_update_only(const StencilArgs& a, float alpha) {
+template <int COH, bool LLG>
+__device__ __forceinline__ double fused_update_only(const StencilArgs& a, float alpha, unsigned tag_in) {
     const long long q = a.g.pitch / 4;
     const long long lo = -q, hi = (long long)(a.g.ny + 1) * q, own = (long long)a.g.ny * q;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -737,6 +770,17 @@ __device__ __forceinline__ double fused_update_only(const StencilArgs& a, float 
             st4(a.r_out + 4 * i, rn);
             st4(a.y + 4 * i, y4);
             st4(a.x + 4 * i, x4);
+            if (LLG) {               // the neighbours' next pass reads this rank's boundary lines of r_out / y as LL words
+                const int xq = (int)(i % q) * 4;
+                if (i < q && a.ll.out_prev) {
+                    ll_store4(a.ll.out_prev + a.ll.at(tag_in + 1u, 1, 0), xq, rn, tag_in + 1u);
+                    ll_store4(a.ll.out_prev + a.ll.at(tag_in + 1u, 1, 1), xq, y4, tag_in + 1u);
+                }
+                if (i >= own - q && a.ll.out_next) {
+                    ll_store4(a.ll.out_next + a.ll.at(tag_in + 1u, 0, 0), xq, rn, tag_in + 1u);
+                    ll_store4(a.ll.out_next + a.ll.at(tag_in + 1u, 0, 1), xq, y4, tag_in + 1u);
+                }
+            }
             s += (double)((rn.x * rn.x + rn.y * rn.y) + (rn.z * rn.z + rn.w * rn.w));
         }
     }
@@ -746,26 +790,30 @@ __device__ __forceinline__ double fused_update_only(const StencilArgs& a, float 
 #ifndef SRPS_FUSED_MINB
 #define SRPS_FUSED_MINB 3
 #endif
-template <int SF, bool FIRST>
+template <int SF, bool FIRST, bool LLG>
 __global__ void __launch_bounds__(SW_NT, SRPS_FUSED_MINB) cg_fused_kernel(const StencilArgs a) {
     __shared__ double wsm[(SW_NT / 32) * 4];
     __shared__ double tot[4];
     if (!a.sc->active) return;
+    // LL ghost tag: the reduction sequence number this pass starts with (rewritten only by this kernel's last block,
+    // after every block has read it: a block takes its reduction ticket after its own work)
+    const unsigned tag_in = LLG ? (unsigned)__ldcg(a.comm.seq) : 0u;
     const float beta = FIRST ? 0.f : a.sc->beta;
     const float alpha = FIRST ? 0.f : a.sc->alpha;          // the step of the previous pass, still pending
     const bool deferred = !FIRST && a.sc->defer != 0;       // uniform over the grid: written by the previous launch
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     if (deferred) {
-        v[0] = fused_update_only<0>(a, alpha);
+        v[0] = fused_update_only<0, LLG>(a, alpha, tag_in);
     } else {
         const LightConsts& lc = c_lc[a.lc_slot];
         double ex[3];
-        v[1] = strip_pass<FIRST ? MODE_FUSED0 : MODE_FUSED, SF>(a, lc, beta, alpha, ex);
+        v[1] = strip_pass<FIRST ? MODE_FUSED0 : MODE_FUSED, SF, 0, LLG>(a, lc, beta, alpha, ex, tag_in);
         v[0] = ex[0]; v[2] = ex[1]; v[3] = ex[2];
     }
     if (!grid_reduce_last4<SW_NT>(v, a.partials, a.ticket, wsm, tot)) return;
-    // strip partition: the neighbours pull their ghost lines of r_out / y out of this rank's planes in the next pass
-    peer_allreduce_small<SW_NT, 4>(a.comm, tot, a.comm.world > 1);
+    // strip partition: the ghost lines travel as self-validating LL words (pushed above), so the reduction is a pure
+    // scalar exchange -- no system-scope fence on the critical path of a pass
+    peer_allreduce_small<SW_NT, 4>(a.comm, tot, false);
     if (threadIdx.x == 0) {
         CgScalars* s = a.sc;
         const double S0 = tot[0], S1 = tot[1], S3 = tot[3];
@@ -955,9 +1003,9 @@ __global__ void __launch_bounds__(SW_NT, SRPS_STRIP_MINB) cg_persistent_kernel(c
 //
 // Single GPU: every block waits for the arrival counter and sums all partials itself (fixed order, no broadcast hop).
 // Strip partition (world > 1): the LAST block to arrive sums the partials, exchanges the four rank totals with the
-// peers (peer_allreduce_small: one NVLink store per peer and word, system-scope release/acquire around it) and
-// publishes the world totals under a generation word; everybody else spins on that word.  The barrier therefore also
-// orders this rank's r / y boundary lines before the neighbours' next pass, which reads them in place (COH = 2).
+// peers (peer_allreduce_small: one NVLink store per peer and word) and publishes the world totals under a generation
+// word; everybody else spins on that word.  The ghost lines of r / y do not depend on this barrier: every pass pushes
+// its boundary lines to the neighbours as self-validating LL words (GhostLL, srps_comm.cuh).
 // ---------------------------------------------------------------------------------------------
 template <bool WORLD>
 __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double (&v)[4], int which, unsigned long long& gen,
@@ -998,7 +1046,7 @@ __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double 
         if (lane == 0) s_tot[wid] = t;
         __syncthreads();
         if (WORLD) {
-            peer_allreduce_small<SW_NT, 4>(a.st.comm, s_tot, true);
+            peer_allreduce_small<SW_NT, 4>(a.st.comm, s_tot, false);      // ghost lines are LL words: pure scalar exchange
             if (threadIdx.x < 4) a.world_tot[(gen & 1ull) * 4 + threadIdx.x] = s_tot[threadIdx.x];
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -1020,7 +1068,7 @@ __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double 
 template <int SF, int COH>
 __global__ void __launch_bounds__(SW_NT, SRPS_FUSED_MINB) cg_persistent_fused_kernel(const PersistentArgs a) {
     static_assert(SW_NT / 32 == 4, "one warp per dot in grid_allreduce4");
-    static_assert(COH == 1 || COH == 2, "planes are rewritten inside this launch: coherent loads");
+    static_assert(COH == 1 || COH == 2, "1: single GPU, 2: strip partition (planes are rewritten inside this launch: coherent loads)");
     constexpr bool WORLD = (COH == 2);
     __shared__ double wsm[(SW_NT / 32) * 4];
     __shared__ double s_tot[4];
@@ -1037,21 +1085,26 @@ __global__ void __launch_bounds__(SW_NT, SRPS_FUSED_MINB) cg_persistent_fused_ke
     unsigned long long gen = 0ull;
     StencilArgs st = a.st;
     st.x = a.x;
+    // LL ghost tags: one all-reduce per executed pass, so pass number `pass` starts with sequence number base + pass
+    const unsigned tag0 = WORLD ? (unsigned)__ldcg(a.st.comm.seq) : 0u;
     for (int pass = 0; pass < a.passes + FUSED_SPARE_PASSES; pass++) {
         st.r = a.rr[pass & 1];   st.r_out = a.rr[(pass + 1) & 1];
         st.y_in = a.yy[pass & 1]; st.y = a.yy[(pass + 1) & 1];
         st.p_in = a.pp[pass & 1]; st.p_out = a.pp[(pass + 1) & 1];
-        if (WORLD) {             // the neighbours' boundary lines of this pass's r / y planes
-            st.r_prev_line = a.r_prev[pass & 1]; st.r_next_line = a.r_next[pass & 1];
-            st.y_prev_line = a.y_prev[pass & 1]; st.y_next_line = a.y_next[pass & 1];
+        if (WORLD) {
+            // pass 0 pulls the ghost lines of r out of the neighbours' planes (written and ordered by the residual kernel,
+            // first touch of those addresses in this launch: nothing stale in L1); later passes read pushed LL words
+            st.r_prev_line = pass == 0 ? a.r_prev[0] : nullptr; st.r_next_line = pass == 0 ? a.r_next[0] : nullptr;
+            st.y_prev_line = nullptr; st.y_next_line = nullptr;
         }
+        const unsigned tag_in = tag0 + (unsigned)pass;
         double v[4] = {0.0, 0.0, 0.0, 0.0};
         if (deferred) {                              // see cg_fused_kernel: apply the step, measure r.r
-            v[0] = fused_update_only<COH>(st, alpha);
+            v[0] = fused_update_only<1, WORLD>(st, alpha, tag_in);
         } else {
             double ex[3];
-            v[1] = (pass == 0) ? strip_pass<MODE_FUSED0, SF, COH>(st, lc, 0.f, 0.f, ex)
-                               : strip_pass<MODE_FUSED, SF, COH>(st, lc, beta, alpha, ex);
+            v[1] = (pass == 0) ? strip_pass<MODE_FUSED0, SF, 1, WORLD>(st, lc, 0.f, 0.f, ex, tag_in)
+                               : strip_pass<MODE_FUSED, SF, 1, WORLD>(st, lc, beta, alpha, ex, tag_in);
             v[0] = ex[0]; v[2] = ex[1]; v[3] = ex[2];
         }
         grid_allreduce4<WORLD>(a, v, pass & 1, gen, wsm, s_tot);

@@ -22,6 +22,7 @@ constexpr int MAX_RANKS = 8;
 constexpr int MB_SLOTS = 4;
 constexpr int MB_VALS = 800;      // doubles per (slot, source rank): lighting needs n*12 <= 768
 constexpr int MB_SMALL = 4;       // doubles per (slot, source rank) on the latency-optimised path (fused CG pass: 4 dots)
+constexpr unsigned SPIN_LIMIT = 1u << 26;   // polls of one word before a waiting thread traps (tens of seconds)
 
 struct Mailbox {
     unsigned long long flag[MB_SLOTS][MAX_RANKS];
@@ -163,7 +164,11 @@ __device__ __forceinline__ void peer_allreduce_small(const PeerComm& c, double* 
         if (release) __threadfence_system();
         st_relaxed_sys_u64(&c.peer[t]->ll[slot][c.rank][w], tag | ((w & 1) ? (bits >> 32) : (bits & 0xffffffffull)));
         unsigned long long v;
-        do { v = ld_relaxed_sys_u64(&c.local->ll[slot][t][w]); } while ((v & 0xffffffff00000000ull) != tag);
+        unsigned spins = 0u;
+        do {
+            v = ld_relaxed_sys_u64(&c.local->ll[slot][t][w]);
+            if (++spins > SPIN_LIMIT) __trap();
+        } while ((v & 0xffffffff00000000ull) != tag);
         got = (unsigned)(v & 0xffffffffull);
         if (!(w & 1)) s_lo[t][w >> 1] = got;
         if (release) __threadfence_system();      // acquire side, see peer_allreduce_scalar
@@ -195,6 +200,49 @@ __device__ __forceinline__ bool grid_reduce_last_world(double v, double* partial
     (void)kernel_pushes;
     total = peer_allreduce_scalar<NT>(c, total, c.world > 1);
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ghost lines of the fused CG pass in LL format (data and flag in ONE 8-byte word, as in the mailbox):
+// every pass PUSHES its two boundary lines of r_out and y into the neighbours' ghost buffers as words
+// {sequence tag | float bits}; the next pass reads them from LOCAL memory and validates each word by its tag.
+// An 8-byte word is written and read by single-copy-atomic accesses, so a reader sees the old word or the new one,
+// never a mix, and needs no ordering against any other location: no system-scope fence and no remote read sits on
+// the critical path of a pass (round 1 pulled the lines over NVLink and ordered them by the all-reduce, which is a
+// release/acquire chain only with two system fences per pass -- measured +4.7 us per pass at 2 GPUs).
+// tag = low 32 bits of the reduction sequence number the CONSUMING pass starts with (one all-reduce per pass, the
+// same count on every rank); slot = tag & 1 (the all-reduce between two passes keeps a writer at most one pass ahead
+// of its reader, so two slots suffice).  Layout: [slot][side][array r|y][pitch] words; side 0 = from the previous
+// rank (this rank's line -1), side 1 = from the next rank (line ny).
+// ---------------------------------------------------------------------------------------------
+struct GhostLL {
+    unsigned long long* in;          // this rank's buffer (nullptr: single GPU)
+    unsigned long long* out_prev;    // the previous rank's buffer as mapped here, or nullptr at the first strip
+    unsigned long long* out_next;    // the next rank's buffer, or nullptr at the last strip
+    int pitch;
+    __device__ __forceinline__ long long at(unsigned tag, int side, int arr) const {
+        return (long long)((((int)(tag & 1u) * 2 + side) * 2 + arr)) * pitch;
+    }
+};
+constexpr size_t ghost_ll_bytes(int pitch) { return (size_t)2 * 2 * 2 * (size_t)pitch * sizeof(unsigned long long); }
+
+__device__ __forceinline__ void ll_store4(unsigned long long* line, int x, const float4& v, unsigned tag) {
+    const unsigned long long t = (unsigned long long)tag << 32;
+    unsigned long long w0 = t | __float_as_uint(v.x), w1 = t | __float_as_uint(v.y);
+    unsigned long long w2 = t | __float_as_uint(v.z), w3 = t | __float_as_uint(v.w);
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(line + x), "l"(w0), "l"(w1) : "memory");
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(line + x + 2), "l"(w2), "l"(w3) : "memory");
+}
+__device__ __forceinline__ float4 ll_load4(const unsigned long long* line, int x, unsigned tag) {
+    unsigned long long w0, w1, w2, w3;
+    unsigned spins = 0u;
+    do {
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(line + x) : "memory");
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(line + x + 2) : "memory");
+        if (++spins > SPIN_LIMIT) __trap();      // a neighbour died or the ranks left lock-step: fail the launch, do not hang the GPU
+    } while ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag || (unsigned)(w2 >> 32) != tag || (unsigned)(w3 >> 32) != tag);
+    return make_float4(__uint_as_float((unsigned)w0), __uint_as_float((unsigned)w1), __uint_as_float((unsigned)w2),
+                       __uint_as_float((unsigned)w3));
 }
 
 // Ghost-line destinations in the neighbours' planes (mapped peer pointers), per plane kind.
