@@ -89,7 +89,11 @@ PngImage read_png(const std::string& path) {
         const unsigned char* data = &f[pos + 8];
         if (pos + 12 + len > f.size()) throw std::runtime_error(path + ": truncated PNG chunk");
         if (type == "IHDR") {
-            img.w = (int)be32(data); img.h = (int)be32(data + 4); img.bits = data[8]; ctype = data[9]; interlace = data[12];
+            if (len < 13) throw std::runtime_error(path + ": bad PNG header");
+            const uint32_t w32 = be32(data), h32 = be32(data + 4);
+            // a dataset image is at most a few thousand pixels wide: anything else is a corrupt header, not an allocation request
+            if (w32 == 0 || h32 == 0 || w32 > 65535u || h32 > 65535u) throw std::runtime_error(path + ": implausible PNG size");
+            img.w = (int)w32; img.h = (int)h32; img.bits = data[8]; ctype = data[9]; interlace = data[12];
         } else if (type == "PLTE") {
             plte.assign(data, data + len);
         } else if (type == "IDAT") {
@@ -99,6 +103,7 @@ PngImage read_png(const std::string& path) {
         }
         pos += 12 + len;
     }
+    if (ctype < 0) throw std::runtime_error(path + ": PNG without a header chunk");
     const int bits = img.bits;
     const bool low = bits == 1 || bits == 2 || bits == 4;
     const bool ok = (ctype == 0 && (low || bits == 8 || bits == 16)) || (ctype == 3 && (low || bits == 8) && !plte.empty()) ||
@@ -252,16 +257,20 @@ struct MatVar { std::vector<int> dims; std::vector<double> data; };
 
 struct Cursor {
     const unsigned char* p; size_t n, pos = 0;
+    // One data element: its payload [data, data + nbytes) is guaranteed to lie inside the buffer on success (a
+    // truncated or corrupt file fails here instead of being read past its end).
     bool tag(uint32_t& type, uint32_t& nbytes, const unsigned char*& data) {
         if (pos + 8 > n) return false;
         uint32_t t; memcpy(&t, p + pos, 4);
-        if (t >> 16) {                                          // small data element
+        if (t >> 16) {                                          // small data element: <= 4 payload bytes inside the tag
             type = t & 0xffff; nbytes = t >> 16; data = p + pos + 4; pos += 8;
-        } else {
-            type = t; memcpy(&nbytes, p + pos + 4, 4); data = p + pos + 8;
-            pos += 8 + (type == 15 ? nbytes : ((nbytes + 7) / 8) * 8);      // miCOMPRESSED elements are not padded
+            return nbytes <= 4;
         }
-        return pos <= n + 7;
+        type = t; memcpy(&nbytes, p + pos + 4, 4); data = p + pos + 8;
+        if ((size_t)nbytes > n - pos - 8) return false;         // payload must fit
+        const size_t adv = 8 + (type == 15 ? (size_t)nbytes : (((size_t)nbytes + 7) / 8) * 8);   // miCOMPRESSED elements are not padded
+        pos = std::min(n, pos + adv);                           // the padding of the last element may be cut off
+        return true;
     }
 };
 
@@ -281,6 +290,8 @@ bool parse_matrix(const unsigned char* p, size_t n, std::string& name, MatVar& v
     name.assign((const char*)d, nb);
     if (!c.tag(type, nb, d)) return false;                      // real part
     var.data.clear();
+    size_t expect = 1;
+    for (int v : var.dims) { if (v < 0 || (v > 0 && expect > (size_t)1 << 40)) return false; expect *= (size_t)v; }
     switch (type) {
         case 1: append_as_double<int8_t>(var.data, d, nb); break;
         case 2: append_as_double<uint8_t>(var.data, d, nb); break;
@@ -292,7 +303,7 @@ bool parse_matrix(const unsigned char* p, size_t n, std::string& name, MatVar& v
         case 9: append_as_double<double>(var.data, d, nb); break;
         default: return false;
     }
-    return true;
+    return var.data.size() == expect;                           // dims and payload must agree
 }
 }  // namespace
 
@@ -311,10 +322,10 @@ void MatFileDataHandler::loadDataFromMatFiles(const char* filename) {
         std::vector<unsigned char> tmp;
         const unsigned char* body = d; size_t blen = nb;
         if (type == 15) {                                       // miCOMPRESSED
-            tmp = inflate_all(d, nb, (size_t)nb * 4);
+            try { tmp = inflate_all(d, nb, (size_t)nb * 4); } catch (...) { continue; }
             if (tmp.size() < 8) continue;
             uint32_t t2, n2; memcpy(&t2, tmp.data(), 4); memcpy(&n2, tmp.data() + 4, 4);
-            if (t2 != 14) continue;
+            if (t2 != 14 || (size_t)n2 > tmp.size() - 8) continue;           // the inner length must fit the inflated data
             body = tmp.data() + 8; blen = n2;
         } else if (type != 14) {
             continue;
@@ -330,21 +341,32 @@ void MatFileDataHandler::loadDataFromMatFiles(const char* filename) {
         }
         return it->second;
     };
+    auto bad = [](const char* what) -> void {
+        fprintf(stderr, "Variable not found, or error reading MAT file\n");          // Utilities.cpp:37-40
+        throw std::runtime_error(std::string("Failed reading MAT file: ") + what);
+    };
     MatVar& vI = need("I");
     if (vI.dims.size() < 4) throw std::runtime_error("MAT variable I must be h x w x c x n");
     I_h = vI.dims[0]; I_w = vI.dims[1]; I_c = vI.dims[2]; I_n = vI.dims[3];            // Utilities.cpp:171
+    if (I_h < 1 || I_w < 1 || I_c < 1 || I_n < 1 || vI.data.size() != (size_t)I_h * I_w * I_c * I_n) bad("I: dims do not match its data");
     I = new float[vI.data.size()];
     for (size_t i = 0; i < vI.data.size(); i++) I[i] = (float)vI.data[i];
     MatVar& vK = need("K");
+    if (vK.data.size() < 9) bad("K must be 3 x 3");
     K = new float[9];
     for (int i = 0; i < 9; i++) K[i] = (float)vK.data[i];
     MatVar& vm = need("mask");
+    if (vm.data.size() != (size_t)I_h * I_w) bad("mask must be h x w");
     mask = new float[(size_t)I_h * I_w];
     for (size_t i = 0; i < (size_t)I_h * I_w; i++) mask[i] = (float)vm.data[i];
-    sf = (float)need("sf").data[0];
+    MatVar& vsf = need("sf");
+    if (vsf.data.empty() || !(vsf.data[0] >= 1.0)) bad("sf must be a scalar >= 1");
+    sf = (float)vsf.data[0];
     MatVar& vz = need("z0");
+    if (vz.dims.size() < 2) bad("z0 must be at least 2-D");
     z0_n = vz.dims.size() > 2 ? vz.dims[2] : 1;                                          // Utilities.cpp:188-190
     z0_h = vz.dims[0]; z0_w = vz.dims[1];
+    if (z0_h < 1 || z0_w < 1 || z0_n < 1 || vz.data.size() != (size_t)z0_h * z0_w * z0_n) bad("z0: dims do not match its data");
     z0 = new float[vz.data.size()];
     for (size_t i = 0; i < vz.data.size(); i++) z0[i] = (float)vz.data[i];
 }

@@ -7,6 +7,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <cmath>
 #include <cstdio>
 #include <cstring>

@@ -235,3 +235,37 @@ def test_png_flavours_load_like_cv_imread(cli, tmp_path):
         assert list(snap["dims"]) == [dh.I_h, dh.I_w, int(dh.sf)], kind
         assert np.array_equal(snap["mask"].astype(bool), mflat), kind
         assert np.array_equal(snap["I"], I), kind
+
+
+def test_truncated_and_corrupt_datasets_fail_cleanly(cli, tmp_path):
+    """Sizes stored in a file are not trusted: a truncated MAT file, a MAT file whose dims disagree with its data and a
+    PNG with an absurd header end in the reference's error exit (Utilities.cpp:37-40, 165-168), not in a crash."""
+    import struct
+    import zlib
+    from scipy.io import savemat
+    folder = write_image_folder(str(tmp_path / "scene"))
+    from srmeetsps_cuda_b200 import ImageDataHandler
+    dh = ImageDataHandler().loadDataFromImages(folder)
+    good = str(tmp_path / "good.mat")
+    payload = {"I": dh.I.transpose(2, 3, 1, 0).astype(np.float64), "K": dh.K.reshape(3, 3, order="F").astype(np.float64),
+               "mask": (dh.mask != 0).astype(np.uint8), "sf": float(dh.sf), "z0": dh.z0.transpose(1, 2, 0).astype(np.float64)}
+    savemat(good, payload, do_compression=False)
+    raw = open(good, "rb").read()
+    cases = {"cut_half.mat": raw[: len(raw) // 2], "cut_tag.mat": raw[:128 + 12], "cut_tail.mat": raw[:-9]}
+    small_mask = dict(payload, mask=payload["mask"][:-1])             # mask is not h x w
+    savemat(str(tmp_path / "badmask.mat"), small_mask, do_compression=True)
+    for name, blob in cases.items():
+        open(str(tmp_path / name), "wb").write(blob)
+    for name in list(cases) + ["badmask.mat"]:
+        res = subprocess.run([cli, "--dstype=matlab", f"--dsloc={tmp_path}/{name}", "--init-only"], capture_output=True, text=True)
+        # 134 = the reference's escaped std::runtime_error (Main.cpp has no handler), returned deliberately; a signal
+        # (negative code: SIGSEGV / SIGABRT from a wild read or a failed huge allocation) is the failure this guards against
+        assert res.returncode == 134 and "MAT file" in res.stderr, (name, res.returncode, res.stderr[-300:])
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    huge = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 0x7fffffff, 0x7fffffff, 8, 0, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0")) + chunk(b"IEND", b"")
+    open(os.path.join(folder, "mask.png"), "wb").write(huge)
+    res = subprocess.run([cli, "--dstype=images", f"--dsloc={folder}", "--init-only"], capture_output=True, text=True)
+    assert res.returncode == 134 and "implausible PNG size" in res.stderr, (res.returncode, res.stderr[-300:])
