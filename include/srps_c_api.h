@@ -154,6 +154,17 @@ int  srps_profile_kernels(srps_ctx* ctx, int reps, float* out_ms);
 /* Test hook: y = (Kt K + G^T M G) p with the M of the current rho/dz/s (masked host vectors). */
 int  srps_apply_depth_operator(srps_ctx* ctx, const float* p_host, float* y_host);
 
+/* ---- one-shot depth pre-processing on the device (the parallel steps of SRPS.cu:117-149; no context needed) ----------
+ * srps_init_depth_mean: mean over `frames` low-resolution depth frames (z0: [frames][n_lr], any pixel order) divided by
+ * the frame count, hole = 1 where any frame is 0 (devicecalls.cu:95-125).  The flagged pixels are then inpainted by the
+ * caller (Telea fast marching, SRPS.cu:133: a sequential front, host code in src/host/Preprocess.cpp).
+ * srps_init_depth_smooth_upsample: depth / max -> cv::bilateralFilter(-1, sigma_color, sigma_space) -> * max (= zs, the
+ * smoothed LR depth, rows x cols) -> cv::resize(INTER_CUBIC) to orows x ocols (= z_full).  Row-major images; the
+ * reference passes its column-major buffers transposed: rows = z0_w, cols = z0_h, orows = I_w, ocols = I_h (SRPS.cu:130-149). */
+int  srps_init_depth_mean(int device, const float* z0, int n_lr, int frames, float* mean_out, unsigned char* hole_out);
+int  srps_init_depth_smooth_upsample(int device, const float* depth, int rows, int cols, int orows, int ocols,
+                                     float sigma_color, float sigma_space, float* zs_out, float* z_full_out);
+
 /* Build identification: "sm_100a;<git or date>" */
 const char* srps_build_info(void);
 

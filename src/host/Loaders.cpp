@@ -21,6 +21,7 @@ int Preferences::blockY = 4;         // Main.cpp:6
 int Preferences::deviceId = 0;       // Main.cpp:7
 int Preferences::albedoMode = 0;
 int Preferences::maxOuter = 0;
+int Preferences::initOnHost = 0;
 
 DataHandler::DataHandler() : I(NULL), K(NULL), mask(NULL), z0(NULL) {}       // Utilities.cpp:142
 DataHandler::~DataHandler() { freeMemory(); }

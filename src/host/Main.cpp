@@ -19,6 +19,7 @@ static void printMessage() {
                  "\t-x, --blockx (value:256)\n\t\tblock dimension x\n"
                  "\t-y, --blocky (value:4)\n\t\tblock dimension y\n"
                  "\textensions: --albedo=closed_form|reference_cg  --iters=K  --init-only  --dump-init=F.snap  --out=F.snap\n"
+                 "\t            --init=device|host (depth pre-processing: CUDA kernels (default) or host cores, e.g. for --init-only without a GPU)\n"
                  "\t            --outdir=DIR (s/rho/z/N.mat + normals/albedo/depth.png)  --render=F.snap (files from a result snapshot, no GPU)\n";
 }
 
@@ -58,6 +59,7 @@ int main(int argc, char* argv[]) {
     Preferences::blockY = atoi(opt["blocky"].c_str());
     Preferences::deviceId = atoi(opt["device"].c_str());
     if (opt.count("albedo")) Preferences::albedoMode = opt["albedo"] == "reference_cg" ? 1 : 0;
+    if (opt.count("init")) Preferences::initOnHost = opt["init"] == "host" ? 1 : 0;
     auto configure = [&](SRPS& s) {
         s.init_only = opt.count("init-only") != 0;
         if (opt.count("dump-init")) s.dump_init = opt["dump-init"];

@@ -11,6 +11,10 @@
 #include <queue>
 #include <vector>
 
+#include <stdexcept>
+#include <string>
+
+#include "../../include/srps_c_api.h"
 #include "Utilities.h"
 
 namespace {
@@ -244,8 +248,26 @@ void resize_cubic(const std::vector<float>& src, int rows, int cols, std::vector
 
 }  // namespace
 
+// Default path: the parallel steps on the device (csrc/srps_init.cuh: mean + flags, max, bilateral, bicubic), the
+// fast-marching inpainting between them on the host.  Same arithmetic as the host path below.
+static void preprocess_depth_device(const float* z0, int z0_h, int z0_w, int z0_n, int I_h, int I_w, std::vector<float>& zs,
+                                    std::vector<float>& z_full) {
+    const int n = z0_h * z0_w;
+    std::vector<float> mean(n);
+    std::vector<unsigned char> hole(n);
+    if (srps_init_depth_mean(Preferences::deviceId, z0, n, z0_n, mean.data(), hole.data()))
+        throw std::runtime_error(std::string("srps_init_depth_mean: ") + srps_last_error(nullptr));
+    const int rows = z0_w, cols = z0_h;                                              // SRPS.cu:130-132
+    inpaint_telea(mean, hole, rows, cols, 16);                                       // SRPS.cu:133
+    zs.resize(n);
+    z_full.resize((size_t)I_w * I_h);
+    if (srps_init_depth_smooth_upsample(Preferences::deviceId, mean.data(), rows, cols, I_w, I_h, 2.f, 2.f, zs.data(), z_full.data()))
+        throw std::runtime_error(std::string("srps_init_depth_smooth_upsample: ") + srps_last_error(nullptr));
+}
+
 void preprocess_depth(const float* z0, int z0_h, int z0_w, int z0_n, int I_h, int I_w, std::vector<float>& zs,
                       std::vector<float>& z_full) {
+    if (!Preferences::initOnHost) return preprocess_depth_device(z0, z0_h, z0_w, z0_n, I_h, I_w, zs, z_full);
     const int n = z0_h * z0_w;
     // mean over the frames, always divided by the frame count; a pixel is flagged if ANY frame is 0 (devicecalls.cu:95-110)
     std::vector<float> mean(n, 0.f);

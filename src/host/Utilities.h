@@ -17,6 +17,8 @@ struct Preferences {
     static int deviceId;
     static int albedoMode;    // extension: 0 closed form (default), 1 the reference's diagonal CG
     static int maxOuter;      // extension: 0 -> the reference's MAX_ITERATIONS = 10
+    static int initOnHost;    // extension (--init=host): depth pre-processing on the host cores instead of the device
+                              // (tooling without a GPU: --init-only dumps); default 0 = device kernels, Telea on the host
 private:
     Preferences() {}
 };

@@ -58,6 +58,9 @@ EXPORTS = {
     "srps_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "srps_profile_kernels": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "srps_apply_depth_operator": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "srps_init_depth_mean": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "srps_init_depth_smooth_upsample": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                                  C.c_void_p, C.c_void_p]),
     "srps_build_info": (C.c_char_p, []),
 }
 

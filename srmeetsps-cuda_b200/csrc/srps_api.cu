@@ -20,6 +20,7 @@
 #include "srps_cg.cuh"
 #include "srps_epilogue.cuh"
 #include "srps_geom.cuh"
+#include "srps_init.cuh"
 #include "srps_stack.cuh"
 
 using namespace srps;
@@ -1247,5 +1248,67 @@ extern "C" int srps_pixel_range(const srps_ctx* ctx, long long* p0, long long* p
     if (p1) *p1 = ctx->pix0 + ctx->npix;
     if (q0) *q0 = ctx->lr0;
     if (q1) *q1 = ctx->lr0 + ctx->npixs;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one-shot depth pre-processing on the device (srps_init.cuh); stateless: temporary buffers only
+// ------------------------------------------------------------------------------------------------
+#define CKI(call)                                                                                                   \
+    do {                                                                                                            \
+        cudaError_t _e = (call);                                                                                    \
+        if (_e != cudaSuccess) {                                                                                    \
+            char _b[512];                                                                                           \
+            snprintf(_b, sizeof _b, "%s:%d: %s -> %s (%d)", __FILE__, __LINE__, #call, cudaGetErrorString(_e), (int)_e); \
+            g_create_error = _b;                                                                                    \
+            for (void* q : bufs) cudaFree(q);                                                                       \
+            return (int)_e;                                                                                         \
+        }                                                                                                           \
+    } while (0)
+
+extern "C" int srps_init_depth_mean(int device, const float* z0, int n_lr, int frames, float* mean_out, unsigned char* hole_out) {
+    if (!z0 || !mean_out || !hole_out || n_lr < 1 || frames < 1) return fail(nullptr, SRPS_E_INVALID, "bad argument");
+    std::vector<void*> bufs;
+    CKI(cudaSetDevice(device));
+    float *d_z0 = nullptr, *d_mean = nullptr; unsigned char* d_hole = nullptr;
+    CKI(cudaMalloc(&d_z0, sizeof(float) * (size_t)n_lr * frames)); bufs.push_back(d_z0);
+    CKI(cudaMalloc(&d_mean, sizeof(float) * (size_t)n_lr)); bufs.push_back(d_mean);
+    CKI(cudaMalloc(&d_hole, (size_t)n_lr)); bufs.push_back(d_hole);
+    CKI(cudaMemcpy(d_z0, z0, sizeof(float) * (size_t)n_lr * frames, cudaMemcpyHostToDevice));
+    depth_mean_kernel<<<(n_lr + INIT_NT - 1) / INIT_NT, INIT_NT>>>(d_z0, n_lr, frames, d_mean, d_hole);
+    CKI(cudaGetLastError());
+    CKI(cudaMemcpy(mean_out, d_mean, sizeof(float) * (size_t)n_lr, cudaMemcpyDeviceToHost));
+    CKI(cudaMemcpy(hole_out, d_hole, (size_t)n_lr, cudaMemcpyDeviceToHost));
+    for (void* q : bufs) cudaFree(q);
+    return 0;
+}
+
+extern "C" int srps_init_depth_smooth_upsample(int device, const float* depth, int rows, int cols, int orows, int ocols,
+                                               float sigma_color, float sigma_space, float* zs_out, float* z_full_out) {
+    if (!depth || !zs_out || !z_full_out || rows < 1 || cols < 1 || orows < 1 || ocols < 1) return fail(nullptr, SRPS_E_INVALID, "bad argument");
+    std::vector<void*> bufs;
+    CKI(cudaSetDevice(device));
+    const int n = rows * cols;
+    const size_t nout = (size_t)orows * ocols;
+    float *d_a = nullptr, *d_b = nullptr, *d_tmp = nullptr, *d_out = nullptr; int* d_mx = nullptr;
+    CKI(cudaMalloc(&d_a, sizeof(float) * (size_t)n)); bufs.push_back(d_a);
+    CKI(cudaMalloc(&d_b, sizeof(float) * (size_t)n)); bufs.push_back(d_b);
+    CKI(cudaMalloc(&d_tmp, sizeof(float) * (size_t)rows * ocols)); bufs.push_back(d_tmp);
+    CKI(cudaMalloc(&d_out, sizeof(float) * nout)); bufs.push_back(d_out);
+    CKI(cudaMalloc(&d_mx, sizeof(int))); bufs.push_back(d_mx);
+    CKI(cudaMemcpy(d_a, depth, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice));
+    CKI(cudaMemset(d_mx, 0, sizeof(int)));
+    const int nb = (n + INIT_NT - 1) / INIT_NT;
+    max_kernel<<<std::min(nb, 1024), INIT_NT>>>(d_a, n, d_mx);                                   // SRPS.cu:137
+    scale_kernel<<<nb, INIT_NT>>>(d_a, n, d_mx, true, d_b);                                       // SRPS.cu:138
+    const int radius = std::max(1, (int)std::lround(sigma_space * 1.5f));
+    bilateral_kernel<<<nb, INIT_NT>>>(d_b, rows, cols, radius, -0.5f / (sigma_color * sigma_color), -0.5f / (sigma_space * sigma_space), d_a);   // :139
+    scale_kernel<<<nb, INIT_NT>>>(d_a, n, d_mx, false, d_b);                                      // SRPS.cu:140
+    cubic_cols_kernel<<<(unsigned)(((size_t)rows * ocols + INIT_NT - 1) / INIT_NT), INIT_NT>>>(d_b, rows, cols, ocols, d_tmp);   // SRPS.cu:149
+    cubic_rows_kernel<<<(unsigned)((nout + INIT_NT - 1) / INIT_NT), INIT_NT>>>(d_tmp, rows, orows, ocols, d_out);
+    CKI(cudaGetLastError());
+    CKI(cudaMemcpy(zs_out, d_b, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
+    CKI(cudaMemcpy(z_full_out, d_out, sizeof(float) * nout, cudaMemcpyDeviceToHost));
+    for (void* q : bufs) cudaFree(q);
     return 0;
 }

@@ -437,14 +437,13 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
             const bool ok = colok && j <= ny;
             const long long off = ok ? (long long)j * pitch + x : 0;
             const float* rs = a.r + off;
-            rs = (ok && j < 0 && a.r_prev_line) ? a.r_prev_line + x : rs;
-            rs = (ok && j == ny && a.r_next_line) ? a.r_next_line + x : rs;
-            const float4 r4 = ld4_coh<COH>(rs);
+            if (MODE == MODE_FUSED0) {      // only the first pass of a solve pulls ghost lines out of the neighbours' planes
+                rs = (ok && j < 0 && a.r_prev_line) ? a.r_prev_line + x : rs;
+                rs = (ok && j == ny && a.r_next_line) ? a.r_next_line + x : rs;
+            }
+            const float4 r4 = ld4_coh<(COH ? 1 : 0)>(rs);
             if (MODE == MODE_FUSED0) { rn = r4; pin = f4zero(); ypn = 0.f; return r4; }       // first pass: p = r
-            const float* ys = a.y_in + off;
-            ys = (ok && j < 0 && a.y_prev_line) ? a.y_prev_line + x : ys;
-            ys = (ok && j == ny && a.y_next_line) ? a.y_next_line + x : ys;
-            const float4 y4 = ld4_coh<COH>(ys);
+            const float4 y4 = ld4_coh<(COH ? 1 : 0)>(a.y_in + off);
             pin = ld4_coh<(COH ? 1 : 0)>(a.p_in + off);
             rn = make_float4(r4.x - alpha * y4.x, r4.y - alpha * y4.y, r4.z - alpha * y4.z, r4.w - alpha * y4.w);
             const float4 pn = make_float4(rn.x + beta * pin.x, rn.y + beta * pin.y, rn.z + beta * pin.z, rn.w + beta * pin.w);
@@ -465,10 +464,14 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
             ypn = (y4.x * pn.x + y4.y * pn.y) + (y4.z * pn.z + y4.w * pn.w);
             return pn;
         };
-        // LLG: this pass's boundary lines of array `arr` (0 = r_out, 1 = y) to the neighbours, for their next pass
-        auto push_boundary = [&](int j, int arr, const float4& v) {
-            if (j == 0 && a.ll.out_prev) ll_store4(a.ll.out_prev + a.ll.at(tag_in + 1u, 1, arr), x, v, tag_in + 1u);
-            if (j == ny - 1 && a.ll.out_next) ll_store4(a.ll.out_next + a.ll.at(tag_in + 1u, 0, arr), x, v, tag_in + 1u);
+        // LLG: this pass's boundary lines of array `arr` (0 = r_out, 1 = y) to the neighbours, for their next pass.
+        // Called only from the two places a boundary line can be (first line of chunk 0, line SW_G - 1 of the last group)
+        // so that no test or store sits inside the batches of loads / stores of the other groups.
+        auto push_first = [&](int arr, const float4& v) {       // this rank's line 0 = the previous rank's ghost line below
+            if (writer && a.ll.out_prev) ll_store4(a.ll.out_prev + a.ll.at(tag_in + 1u, 1, arr), x, v, tag_in + 1u);
+        };
+        auto push_last = [&](int arr, const float4& v) {        // this rank's line ny-1 = the next rank's ghost line above
+            if (writer && a.ll.out_next) ll_store4(a.ll.out_next + a.ll.at(tag_in + 1u, 0, arr), x, v, tag_in + 1u);
         };
         // z is read and written by this kernel (each float4 by its owner only): coherent load, clamped like the others
         auto load_x = [&](int j) -> float4 {
@@ -480,7 +483,6 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
             if (writer && j < jB) {
                 const long long off = (long long)j * pitch + x;
                 st4(a.r_out + off, rn);
-                if (LLG) push_boundary(j, 0, rn);
                 if (MODE == MODE_FUSED)
                     st4(a.x + off, make_float4(xo.x + alpha * pin.x, xo.y + alpha * pin.y, xo.z + alpha * pin.z, xo.w + alpha * pin.w));
                 s_rr += (double)((rn.x * rn.x + rn.y * rn.y) + (rn.z * rn.z + rn.w * rn.w));
@@ -514,6 +516,7 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
             if (FUSED) { pl[0] = load_fused(jA, r0, pin0, yp0); if (MODE == MODE_FUSED) x0 = load_x(jA); } else pl[0] = load_pn(jA);
             tl[0] = load_t(jA); load_w(jA, wl0[0], wl1[0], wl2[0]);
             if (FUSED) store_owned(jA, r0, x0, pin0, yp0);
+            if (LLG && jA == 0) push_first(0, r0);
             const float left = __shfl_up_sync(FULL, pprev.w, 1), right = __shfl_down_sync(FULL, pprev.x, 1);
             const float xx = (float)(g.jb0 + jA - 1) - g.cx;
             const LineQ q = line_q(lc, g.fx, g.fy, xx, yy0, tp & 0xfbfbfbfbu /* backward x-rows not needed */, pprev, f4zero(),
@@ -528,19 +531,21 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
 #pragma unroll
             for (int l = 1; l <= SW_G; l++) {
                 if (FUSED) {
-                    if (LLG && MODE == MODE_FUSED && l == SW_G && j0 + SW_G == ny && a.comm.rank + 1 < a.comm.world)
-                        pl[l] = load_ghost(1, ny, rn[l], pin[l], ypn[l]);        // the ghost line below the strip (warp-uniform branch)
-                    else
-                        pl[l] = load_fused(j0 + l, rn[l], pin[l], ypn[l]);
+                    pl[l] = load_fused(j0 + l, rn[l], pin[l], ypn[l]);
                     xo[l] = (MODE == MODE_FUSED) ? load_x(j0 + l) : f4zero();
                 } else {
                     pl[l] = load_pn(j0 + l);
                 }
                 tl[l] = load_t(j0 + l); load_w(j0 + l, wl0[l], wl1[l], wl2[l]);
             }
+            if (LLG && MODE == MODE_FUSED && j0 + SW_G == ny && a.comm.rank + 1 < a.comm.world)
+                // the ghost line below the strip comes from the LL buffer (the unconditional load above read the local guard
+                // line): one warp-uniform branch AFTER the batch of loads, in the last group of the strip only
+                pl[SW_G] = load_ghost(1, ny, rn[SW_G], pin[SW_G], ypn[SW_G]);
             if (FUSED) {                        // after the whole batch of loads: stores inside it would serialise them
 #pragma unroll
                 for (int l = 1; l <= SW_G; l++) store_owned(j0 + l, rn[l], xo[l], pin[l], ypn[l]);
+                if (LLG && j0 + SW_G == ny) push_last(0, rn[SW_G - 1]);
             }
             if (KEEPS_P && a.comm.world > 1 && j0 + SW_G >= ny && writer) {      // ghost line below: keep p there too
 #pragma unroll
@@ -595,7 +600,8 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
                 if (writer && j < jB) {
                     const long long off = (long long)j * pitch + x;
                     st4(a.y + off, out);
-                    if (LLG) push_boundary(j, 1, out);
+                    if (LLG && l == 0 && j == 0) push_first(1, out);
+                    if (LLG && l == SW_G - 1 && j == ny - 1) push_last(1, out);
                     if (KEEPS_P) { st4(a.p_out + off, pc); dot += (double)dl; }
                     if (FUSED) s_yy += (double)dyy;
                 }

@@ -41,7 +41,7 @@ def write_image_folder(root, h=48, w=64, sf=2, n=4, seed=0, dropout=0.0):
 
 
 def run_init(cli, dstype, dsloc, out):
-    res = subprocess.run([cli, f"--dstype={dstype}", f"--dsloc={dsloc}", "--init-only", f"--dump-init={out}"],
+    res = subprocess.run([cli, f"--dstype={dstype}", f"--dsloc={dsloc}", "--init-only", "--init=host", f"--dump-init={out}"],
                          capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     lines = res.stdout.splitlines()
@@ -257,7 +257,7 @@ def test_truncated_and_corrupt_datasets_fail_cleanly(cli, tmp_path):
     for name, blob in cases.items():
         open(str(tmp_path / name), "wb").write(blob)
     for name in list(cases) + ["badmask.mat"]:
-        res = subprocess.run([cli, "--dstype=matlab", f"--dsloc={tmp_path}/{name}", "--init-only"], capture_output=True, text=True)
+        res = subprocess.run([cli, "--dstype=matlab", f"--dsloc={tmp_path}/{name}", "--init-only", "--init=host"], capture_output=True, text=True)
         # 134 = the reference's escaped std::runtime_error (Main.cpp has no handler), returned deliberately; a signal
         # (negative code: SIGSEGV / SIGABRT from a wild read or a failed huge allocation) is the failure this guards against
         assert res.returncode == 134 and "MAT file" in res.stderr, (name, res.returncode, res.stderr[-300:])
@@ -267,5 +267,5 @@ def test_truncated_and_corrupt_datasets_fail_cleanly(cli, tmp_path):
 
     huge = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 0x7fffffff, 0x7fffffff, 8, 0, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0")) + chunk(b"IEND", b"")
     open(os.path.join(folder, "mask.png"), "wb").write(huge)
-    res = subprocess.run([cli, "--dstype=images", f"--dsloc={folder}", "--init-only"], capture_output=True, text=True)
+    res = subprocess.run([cli, "--dstype=images", f"--dsloc={folder}", "--init-only", "--init=host"], capture_output=True, text=True)
     assert res.returncode == 134 and "implausible PNG size" in res.stderr, (res.returncode, res.stderr[-300:])
