@@ -18,6 +18,7 @@
 
 #include "../../include/srps_c_api.h"
 #include "srps_cg.cuh"
+#include "srps_cg_tma.cuh"
 #include "srps_epilogue.cuh"
 #include "srps_geom.cuh"
 #include "srps_init.cuh"
@@ -71,6 +72,7 @@ struct srps_ctx {
     int use_persistent = 0, grid_persistent = 0;      // all CG passes in one cooperative launch
     int use_persistent_fused = 0;                     // ... in the fused form (one grid barrier per pass; opt-in)
     int use_fused = 0;                                // one kernel per CG pass (cg_fused_kernel)
+    int use_tma = 0;                                  // ... with the TMA-fed shared-memory ring (cg_fused_tma_kernel) for passes >= 1
     int lc_slot = -1;                                 // this context's slot of the constant-bank lighting constants (c_lc)
     unsigned long long* sync_words = nullptr;         // [0] grid barrier counter, [1] world generation, [2..9] world totals (as double)
     long long n4 = 0;
@@ -182,6 +184,12 @@ static const void* fn_fused_t(int sf) {
 static const void* fn_fused(int sf, bool first, bool world) {       // world: strip partition (LL ghost lines)
     if (world) return first ? fn_fused_t<true, true>(sf) : fn_fused_t<false, true>(sf);
     return first ? fn_fused_t<true, false>(sf) : fn_fused_t<false, false>(sf);
+}
+static const void* fn_fused_tma(int sf, bool world) {
+    if (world) return sf == 1 ? (const void*)cg_fused_tma_kernel<1, true> : (sf == 2 ? (const void*)cg_fused_tma_kernel<2, true>
+                                                                                   : (const void*)cg_fused_tma_kernel<4, true>);
+    return sf == 1 ? (const void*)cg_fused_tma_kernel<1, false> : (sf == 2 ? (const void*)cg_fused_tma_kernel<2, false>
+                                                                          : (const void*)cg_fused_tma_kernel<4, false>);
 }
 static const void* fn_persistent(int sf) {
     return sf == 1 ? (const void*)cg_persistent_kernel<1> : (sf == 2 ? (const void*)cg_persistent_kernel<2> : (const void*)cg_persistent_kernel<4>);
@@ -381,13 +389,24 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
             ctx->use_persistent_fused = ctx->use_persistent = occ_p > 0;
         }
         ctx->use_fused = ctx->use_strip && !ctx->use_persistent && !(cgm && strcmp(cgm, "graph") == 0);
+        // SRPS_CG=fused_tma: the fused pass with bulk-async-copy staging (srps_cg_tma.cuh); 96 KB of dynamic shared memory
+        int occ_tma = 0;
+        if (ctx->use_fused && cgm && strcmp(cgm, "fused_tma") == 0) {
+            const void* ft = fn_fused_tma(sfk, ctx->world > 1);
+            CK(cudaFuncSetAttribute(ft, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tma, ft, SW_NT, TMA_SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); occ_tma = 0; }
+            ctx->use_tma = occ_tma > 0;
+        }
         // one strip geometry for all CG forms of this context: the occupancy of the instances that can be launched
         // (the <sf> instances, not a representative: a cooperative grid sized by another instance's occupancy could
         //  exceed what is resident at once)
         occ = std::max(1, std::min({occupancy(fn_strip_iter(sfk), SW_NT), occupancy(fn_fused(sfk, false, ctx->world > 1), SW_NT),
                                     occupancy(fn_fused(sfk, true, ctx->world > 1), SW_NT), ctx->use_persistent ? occ_p : 1 << 20}));
+        if (ctx->use_tma) occ = std::min(occ, occ_tma);    // the ring kernel is shared-memory bound: 2 CTAs per SM
         const int warps = ctx->sm_count * occ * (SW_NT / 32);
-        int cl = (int)(((long long)g.ny * ctx->strip_n + warps - 1) / warps);
+        // one (strip, chunk) item per resident warp: as many chunks per strip as the warps allow, then the chunk length
+        const int chunks_max = std::max(1, warps / ctx->strip_n);
+        int cl = (g.ny + chunks_max - 1) / chunks_max;
         cl = std::min(256, std::max(8, round_up(cl, SW_G)));
         ctx->strip_cl = cl;
         ctx->strip_chunks = (g.ny + cl - 1) / cl;
@@ -859,6 +878,11 @@ static void set_fused_pass(srps_ctx* ctx, StencilArgs& sa, int k) {
 
 static int launch_fused_pass(srps_ctx* ctx, const StencilArgs& sa, bool first) {
     void* kargs[] = {(void*)&sa};
+    if (ctx->use_tma && !first) {        // the first pass of a solve (no pending step, no y / p operands) keeps the register kernel
+        CK(cudaLaunchKernel(fn_fused_tma(ctx->g.sf, ctx->world > 1), dim3(ctx->grid_strip), dim3(SW_NT), kargs, TMA_SMEM_BYTES, ctx->stream));
+        ctx->launches++;
+        return 0;
+    }
     CK(cudaLaunchKernel(fn_fused(ctx->g.sf, first, ctx->world > 1), dim3(ctx->grid_strip), dim3(SW_NT), kargs, 0, ctx->stream));
     ctx->launches++;
     return 0;

@@ -744,8 +744,7 @@ __device__ __forceinline__ bool grid_reduce_last4(const double (&v)[4], double* 
     __syncthreads();
     if (!s_last4) return false;
     __threadfence();
-    double acc = 0.0;                       // warp `wid` sums value `wid` over the blocks: fixed order
-    for (int b = lane; b < (int)gridDim.x; b += 32) acc += __ldcg(partials + (long long)b * 4 + wid);
+    double acc = lane_strided_sum(partials, (int)gridDim.x, 4, wid, lane);      // warp `wid` sums value `wid` over the blocks: fixed order
     acc = warp_sum(acc);
     if (lane == 0) tot[wid] = acc;
     if (threadIdx.x == 0) *ticket = 0u;
@@ -793,6 +792,41 @@ __device__ __forceinline__ double fused_update_only(const StencilArgs& a, float 
     return s;
 }
 
+// alpha, beta, k, active, defer of the next pass from the four world totals of this one (one thread per rank; identical
+// bits on every rank).  tot = {r.r, p.y, y_prev.p, y.y}; `beta`, `deferred`: what this pass ran with.
+__device__ __forceinline__ void fused_pass_scalars(const StencilArgs& a, const double* tot, float beta, bool deferred) {
+    CgScalars* s = a.sc;
+    const double S0 = tot[0], S1 = tot[1], S3 = tot[3];
+    const double S2 = S1 - (double)beta * tot[2];          // r.y, see the header comment
+    if (s->profile) {                        // srps_profile_kernels: scalars stay as the host set them
+        s->k += 1;
+    } else if (!((float)S0 > s->tol2)) {     // the reference left its loop before this pass (devicecalls.cu:252)
+        s->r1 = S0;
+        s->alpha = 0.f;                      // nothing pending: the previous step went into z above
+        s->active = 0;
+        s->defer = 0;
+    } else if (deferred) {                   // S0 is the measured r1 of the reference's loop
+        s->beta = (float)S0 / (float)s->r0;                                    // devicecalls.cu:262
+        s->r1 = S0;
+        s->alpha = 0.f;                      // applied above
+        s->defer = 0;
+        s->n_defer += 1;
+    } else {
+        const float al = (float)S0 / (float)S1;                                // devicecalls.cu:269
+        const double rr = S0 - 2.0 * (double)al * S2 + (double)al * (double)al * S3;
+        const bool cancelled = !(rr > FUSED_DEFER_REL * S0);                   // also catches a non-finite rr
+        s->dot = S1;
+        s->alpha = al;
+        s->r0 = S0;
+        s->r1 = rr;
+        s->beta = cancelled ? 0.f : (float)rr / (float)S0;                     // devicecalls.cu:262
+        s->defer = cancelled ? 1 : 0;
+        s->k += 1;
+        s->plane = a.plane;
+        s->active = (s->k <= s->max_iter);                                     // devicecalls.cu:252 (k part)
+    }
+}
+
 #ifndef SRPS_FUSED_MINB
 #define SRPS_FUSED_MINB 3
 #endif
@@ -820,38 +854,7 @@ __global__ void __launch_bounds__(SW_NT, SRPS_FUSED_MINB) cg_fused_kernel(const 
     // strip partition: the ghost lines travel as self-validating LL words (pushed above), so the reduction is a pure
     // scalar exchange -- no system-scope fence on the critical path of a pass
     peer_allreduce_small<SW_NT, 4>(a.comm, tot, false);
-    if (threadIdx.x == 0) {
-        CgScalars* s = a.sc;
-        const double S0 = tot[0], S1 = tot[1], S3 = tot[3];
-        const double S2 = S1 - (double)beta * tot[2];          // r.y, see the header comment
-        if (s->profile) {                        // srps_profile_kernels: scalars stay as the host set them
-            s->k += 1;
-        } else if (!((float)S0 > s->tol2)) {     // the reference left its loop before this pass (devicecalls.cu:252)
-            s->r1 = S0;
-            s->alpha = 0.f;                      // nothing pending: the previous step went into z above
-            s->active = 0;
-            s->defer = 0;
-        } else if (deferred) {                   // S0 is the measured r1 of the reference's loop
-            s->beta = (float)S0 / (float)s->r0;                                    // devicecalls.cu:262
-            s->r1 = S0;
-            s->alpha = 0.f;                      // applied above
-            s->defer = 0;
-            s->n_defer += 1;
-        } else {
-            const float al = (float)S0 / (float)S1;                                // devicecalls.cu:269
-            const double rr = S0 - 2.0 * (double)al * S2 + (double)al * (double)al * S3;
-            const bool cancelled = !(rr > FUSED_DEFER_REL * S0);                   // also catches a non-finite rr
-            s->dot = S1;
-            s->alpha = al;
-            s->r0 = S0;
-            s->r1 = rr;
-            s->beta = cancelled ? 0.f : (float)rr / (float)S0;                     // devicecalls.cu:262
-            s->defer = cancelled ? 1 : 0;
-            s->k += 1;
-            s->plane = a.plane;
-            s->active = (s->k <= s->max_iter);                                     // devicecalls.cu:252 (k part)
-        }
-    }
+    if (threadIdx.x == 0) fused_pass_scalars(a, tot, beta, deferred);
 }
 
 // z += alpha p of the last valid pass (alpha == 0: the last pass was void or no pass ran)
@@ -894,8 +897,8 @@ struct PersistentArgs {
     double* part[2];                // per-block partials: the two reductions of a pass (gridDim.x doubles each) / fused form:
                                     // the four dots of a pass, buffers alternating between passes (4 * gridDim.x doubles each)
     double* world_tot;              // two-barrier form: [4] world totals published by block 0, slot gen & 3;
-                                    // fused form: [2][4] the four world totals of a pass, slot gen & 1 (strip partition)
-    unsigned long long* world_gen;  // generation of the last published world total
+                                    // fused form: eight broadcast words {sequence tag | half of a world total} (strip partition)
+    unsigned long long* world_gen;  // two-barrier form: generation of the last published world total
     // strip partition, fused form: the neighbours' boundary lines of the two r and the two y planes (read in place)
     const float* r_prev[2]; const float* r_next[2];
     const float* y_prev[2]; const float* y_next[2];
@@ -1015,9 +1018,10 @@ __global__ void __launch_bounds__(SW_NT, SRPS_STRIP_MINB) cg_persistent_kernel(c
 // ---------------------------------------------------------------------------------------------
 template <bool WORLD>
 __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double (&v)[4], int which, unsigned long long& gen,
-                                                double* wsm /* [SW_NT/32][4] */, double* s_tot /* [4] */) {
+                                                double* wsm /* [SW_NT/32][4] */, double* s_tot /* [4] */, unsigned long long seq) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     __shared__ int s_islast;
+    __shared__ unsigned s_half[8];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const double s = warp_sum(v[i]);
@@ -1043,27 +1047,45 @@ __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double 
     }
     __syncthreads();
     gen += 1ull;
-    if (!WORLD || s_islast) {
-        // warp `wid` sums value `wid` over the blocks in a fixed order (SW_NT / 32 == 4 warps)
-        if (WORLD) __threadfence();
-        double t = 0.0;
-        for (int i = lane; i < (int)gridDim.x; i += 32) t += __ldcg(a.part[which] + (long long)i * 4 + wid);
-        t = warp_sum(t);
+    if (!WORLD) {
+        // every block sums all partials itself: warp `wid` sums value `wid` over the blocks in the fixed order
+        const double t = warp_sum(lane_strided_sum(a.part[which], (int)gridDim.x, 4, wid, lane));
         if (lane == 0) s_tot[wid] = t;
         __syncthreads();
-        if (WORLD) {
-            peer_allreduce_small<SW_NT, 4>(a.st.comm, s_tot, false);      // ghost lines are LL words: pure scalar exchange
-            if (threadIdx.x < 4) a.world_tot[(gen & 1ull) * 4 + threadIdx.x] = s_tot[threadIdx.x];
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                __threadfence();
-                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.world_gen), "l"(gen) : "memory");
-            }
-        }
     } else {
-        if (threadIdx.x == 0) { while (ld_acquire_gpu(a.world_gen) < gen) { } }
-        __syncthreads();
-        if (threadIdx.x < 4) s_tot[threadIdx.x] = __ldcg(a.world_tot + (gen & 1ull) * 4 + threadIdx.x);
+        // The last block to arrive sums the partials, exchanges the four rank totals with the peers and broadcasts the
+        // world totals to the other blocks of this GPU as eight self-validating words {tag | half a double} (one store
+        // each, no flag + fence + data round trip); everybody else polls those eight words with one 64-byte request.
+        const unsigned long long tagw = (seq & 0xffffffffull) << 32;
+        unsigned long long* bc = reinterpret_cast<unsigned long long*>(a.world_tot);
+        if (s_islast) {
+            __threadfence();
+            const double t = warp_sum(lane_strided_sum(a.part[which], (int)gridDim.x, 4, wid, lane));
+            if (lane == 0) s_tot[wid] = t;
+            __syncthreads();
+            peer_allreduce_small<SW_NT, 4>(a.st.comm, s_tot, false, seq);      // ghost lines are LL words: pure scalar exchange
+            if (threadIdx.x < 8) {
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(s_tot[threadIdx.x >> 1]);
+                st_relaxed_sys_u64(bc + threadIdx.x, tagw | ((threadIdx.x & 1) ? (bits >> 32) : (bits & 0xffffffffull)));
+            }
+        } else {
+            if (threadIdx.x < 8) {
+                unsigned long long w;
+                unsigned spins = 0u;
+                do {
+                    w = ld_relaxed_sys_u64(bc + threadIdx.x);
+                    if (++spins > SPIN_LIMIT) __trap();
+                } while ((w & 0xffffffff00000000ull) != tagw);
+                s_half[threadIdx.x] = (unsigned)(w & 0xffffffffull);
+                // acquire: the other blocks' r / y / p of this pass (fenced before their arrival, which the broadcasting
+                // block observed) must be what the next pass reads -- this also drops this SM's stale L1 lines
+                __threadfence();
+            }
+            __syncthreads();
+            if (threadIdx.x < 4)
+                s_tot[threadIdx.x] = __longlong_as_double((long long)((unsigned long long)s_half[2 * threadIdx.x] |
+                                                                      ((unsigned long long)s_half[2 * threadIdx.x + 1] << 32)));
+        }
         __syncthreads();
     }
 #pragma unroll
@@ -1092,7 +1114,7 @@ __global__ void __launch_bounds__(SW_NT, SRPS_FUSED_MINB) cg_persistent_fused_ke
     StencilArgs st = a.st;
     st.x = a.x;
     // LL ghost tags: one all-reduce per executed pass, so pass number `pass` starts with sequence number base + pass
-    const unsigned tag0 = WORLD ? (unsigned)__ldcg(a.st.comm.seq) : 0u;
+    const unsigned long long tag0 = WORLD ? __ldcg(a.st.comm.seq) : 0ull;
     for (int pass = 0; pass < a.passes + FUSED_SPARE_PASSES; pass++) {
         st.r = a.rr[pass & 1];   st.r_out = a.rr[(pass + 1) & 1];
         st.y_in = a.yy[pass & 1]; st.y = a.yy[(pass + 1) & 1];
@@ -1103,7 +1125,7 @@ __global__ void __launch_bounds__(SW_NT, SRPS_FUSED_MINB) cg_persistent_fused_ke
             st.r_prev_line = pass == 0 ? a.r_prev[0] : nullptr; st.r_next_line = pass == 0 ? a.r_next[0] : nullptr;
             st.y_prev_line = nullptr; st.y_next_line = nullptr;
         }
-        const unsigned tag_in = tag0 + (unsigned)pass;
+        const unsigned tag_in = (unsigned)(tag0 + (unsigned long long)pass);
         double v[4] = {0.0, 0.0, 0.0, 0.0};
         if (deferred) {                              // see cg_fused_kernel: apply the step, measure r.r
             v[0] = fused_update_only<1, WORLD>(st, alpha, tag_in);
@@ -1113,7 +1135,7 @@ __global__ void __launch_bounds__(SW_NT, SRPS_FUSED_MINB) cg_persistent_fused_ke
                                : strip_pass<MODE_FUSED, SF, 1, WORLD>(st, lc, beta, alpha, ex, tag_in);
             v[0] = ex[0]; v[2] = ex[1]; v[3] = ex[2];
         }
-        grid_allreduce4<WORLD>(a, v, pass & 1, gen, wsm, s_tot);
+        grid_allreduce4<WORLD>(a, v, pass & 1, gen, wsm, s_tot, (unsigned long long)tag0 + (unsigned long long)pass + 1ull);
         const double S0 = v[0], S1 = v[1], S3 = v[3];
         if (!((float)S0 > tol2)) {                   // void pass, see cg_fused_kernel
             r1 = S0;

@@ -144,16 +144,20 @@ __device__ __forceinline__ double peer_allreduce_scalar(const PeerComm& c, doubl
 
 // The same for NV <= MB_SMALL values at once (the four dot products of a fused CG pass): thread (r, w) sends word w to
 // rank r and waits for rank r's word w.  vals: shared memory of the calling block, world totals on return.
+// seq_known != 0: the caller knows the sequence number of this reduction (persistent CG: start value + pass), which
+// saves the dependent L2 read of the counter on the critical path of a pass.
 template <int NT, int NV>
-__device__ __forceinline__ void peer_allreduce_small(const PeerComm& c, double* vals, bool release) {
+__device__ __forceinline__ void peer_allreduce_small(const PeerComm& c, double* vals, bool release, unsigned long long seq_known = 0ull) {
     static_assert(NV <= MB_SMALL && MAX_RANKS * 2 * NV <= NT, "one thread per (rank, word)");
     if (c.world <= 1) return;
     __shared__ double s_part[MAX_RANKS][NV];
     __shared__ unsigned s_lo[MAX_RANKS][NV];
     __shared__ unsigned long long s_seqn;
-    if (threadIdx.x == 0) s_seqn = __ldcg(c.seq) + 1ull;   // L2: the previous caller may have been another block
-    __syncthreads();
-    const unsigned long long seq = s_seqn;
+    if (seq_known == 0ull) {
+        if (threadIdx.x == 0) s_seqn = __ldcg(c.seq) + 1ull;   // L2: the previous caller may have been another block
+        __syncthreads();
+    }
+    const unsigned long long seq = seq_known ? seq_known : s_seqn;
     const unsigned long long tag = (seq & 0xffffffffull) << 32;
     const int slot = (int)(seq & (MB_SLOTS - 1));
     const int t = threadIdx.x / (2 * NV), w = threadIdx.x % (2 * NV);

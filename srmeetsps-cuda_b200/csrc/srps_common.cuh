@@ -141,6 +141,24 @@ __device__ __forceinline__ bool grid_reduce_last(double v, double* partials, uns
     return true;
 }
 
+// Sum of partials[b * stride + off], b = lane, lane + 32, ... < n, in that order (the fixed order every reduction of
+// this library uses), with eight independent L2 loads in flight per lane: the final sum of a single-pass grid
+// reduction sits on the critical path of every CG pass.
+__device__ __forceinline__ double lane_strided_sum(const double* partials, int n, int stride, int off, int lane) {
+    double acc = 0.0;
+    for (int b0 = 0; b0 < n; b0 += 32 * 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int b = b0 + u * 32 + lane;
+            v[u] = b < n ? __ldcg(partials + (long long)b * stride + off) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc += v[u];      // adding 0.0 for b >= n leaves the sum unchanged
+    }
+    return acc;
+}
+
 // q = M (dxp, dyp, pc) with M = T Q T^T, Q = sum_c w_c S3_c, T = [[fx,0,-xx],[0,fy,-yy],[0,0,-1]]
 // (the reference's rows (rho_c/dz)[fx s0 - xx s2, fy s1 - yy s2, -s2],
 //  devicecalls.cu:583-620, folded over images and channels).

@@ -185,19 +185,19 @@ def test_outer_iterations_match_oracle(cfg, albedo_mode):
     ctx.close()
 
 
-@pytest.mark.parametrize("stencil", ["persistent", "strip", "tile", "fused", "persistent_fused"])
+@pytest.mark.parametrize("stencil", ["persistent", "strip", "tile", "fused", "persistent_fused", "fused_tma"])
 @pytest.mark.parametrize("albedo_mode", ["closed_form", "reference_cg"])
 @pytest.mark.parametrize("cfg", SCENES, ids=lambda c: f"{c['h']}x{c['w']}sf{c['sf']}{c['mask_kind']}")
 def test_each_iteration_from_synchronised_state(cfg, albedo_mode, stencil, monkeypatch):
     """Sharp per-iteration parity: before every outer iteration the CUDA state is set to the oracle's
     (s, rho, z -> normals), so nothing accumulates; one pass of the loop body must then agree to
     fp32 round-off: depth rel. RMSE <= 2e-5, albedo max-abs <= 3e-4, energy 2e-3, same CG pass count.
-    Five CG drivers: one persistent cooperative kernel per solve (default on small scenes), the two-kernel CUDA graph
-    with the warp-strip operator, the same with the shared-memory tile operator, the fused one-kernel-per-pass form
-    (default on large scenes) and the fused form inside one cooperative launch (sf 8/16 scenes fall back to the tile
-    operator in every case)."""
+    Six CG drivers: one persistent cooperative kernel per solve, the two-kernel CUDA graph with the warp-strip
+    operator, the same with the shared-memory tile operator, the fused one-kernel-per-pass form (default on large
+    scenes), the fused form inside one cooperative launch (default on small scenes) and the fused pass fed by bulk
+    async copies through a shared-memory ring (fused_tma); sf 8/16 scenes fall back to the tile operator in every case."""
     monkeypatch.setenv("SRPS_STENCIL", "tile" if stencil == "tile" else "strip")
-    monkeypatch.setenv("SRPS_CG", stencil if stencil in ("persistent", "fused", "persistent_fused") else "graph")
+    monkeypatch.setenv("SRPS_CG", stencil if stencil in ("persistent", "fused", "persistent_fused", "fused_tma") else "graph")
     sc = scene(cfg)
     ctx = make_ctx(sc, albedo_mode=albedo_mode)
     st = oracle_state(sc)
@@ -394,7 +394,7 @@ def test_baseline_sizes_match_oracle(cfg):
     ctx.close()
 
 
-@pytest.mark.parametrize("driver", ["fused", "persistent_fused"])
+@pytest.mark.parametrize("driver", ["fused", "persistent_fused", "fused_tma"])
 def test_fused_cg_guard_on_early_convergence(driver, monkeypatch):
     """sf = 1 with dark images: Kt K = I dominates the operator, the depth CG converges within a few passes and its last
     steps remove almost the whole residual -- the expanded |r - alpha y|^2 of the fused recurrence cancels there.  The
