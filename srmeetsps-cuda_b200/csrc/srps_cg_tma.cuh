@@ -69,7 +69,7 @@ __device__ __forceinline__ double strip_pass_tma(const StencilArgs& a, const Lig
         const bool writer = (lane >= 1) && (lane <= SW_COLS) && colok;
         const int jA = chunk * a.strip_cl;
         const int jB = min(jA + a.strip_cl, ny);
-        const int ngroups = (jB - jA) / SW_G;
+        const int ngroups = (jB - jA + SW_G - 1) / SW_G;      // ny is a multiple of sf only: the last group of the grid may be partial
         const float yy0 = (float)(g.ib0 + x) - g.cy;
 
         // lanes 0..23 copy one (array, line) segment of 512 bytes each; a segment may run past the line pitch into the next
@@ -81,7 +81,9 @@ __device__ __forceinline__ double strip_pass_tma(const StencilArgs& a, const Lig
             if (lane == 0) mbar_arrive_expect_tx(bars + stage, TMA_STAGE_BYTES);
             __syncwarp();
             if (lane < TMA_ARR * SW_G)
-                bulk_g2s(ring + ((stage * TMA_ARR + c_arr) * SW_G + c_line) * 32, c_src + (long long)(j_first + c_line) * pitch + x0w,
+                // lines beyond the guard line ny (partial last group) are never an output line nor the neighbour of one:
+                // copy the guard line in their place, which keeps every copy inside the plane
+                bulk_g2s(ring + ((stage * TMA_ARR + c_arr) * SW_G + c_line) * 32, c_src + (long long)min(j_first + c_line, ny) * pitch + x0w,
                          TMA_LINE_BYTES, bars + stage);
         };
         issue(gcount, jA + 1);

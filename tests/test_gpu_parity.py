@@ -41,6 +41,7 @@ SCENES = [
                                                                                # lighting barely constrained, free-running noise up to 5e-3
     dict(h=272, w=48, sf=16, n=9, seed=8, mask_kind="full"),        # 3 tiles along the contiguous axis, 2 image groups
     dict(h=300, w=40, sf=4, n=17, seed=9, mask_kind="ellipse"),     # partial last tile, 3 image groups (8+8+1)
+    dict(h=64, w=50, sf=2, n=5, seed=14, mask_kind="full"),         # 50 lines: the last 4-line group of the warp-strip kernels is partial
 ]
 
 
