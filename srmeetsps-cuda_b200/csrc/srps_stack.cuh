@@ -48,7 +48,22 @@ template <> __device__ __forceinline__ float4 ld_stack4<unsigned char>(const uns
 // generic multi-value single-pass grid reduction (values as float per thread, partials as double)
 // Returns true in the last block; totals[0..NV) then valid in shared memory `tot`.
 // ---------------------------------------------------------------------------------------------
-template <int NT, int NV>
+// partials[0], partials[stride], ... (n terms) summed in that order with eight independent L2 loads in flight: the
+// last block of a reduction is a serial tail of the whole phase
+__device__ __forceinline__ double ordered_sum(const double* partials, int n, int stride) {
+    double b = 0.0;
+    for (int k0 = 0; k0 < n; k0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = (k0 + u < n) ? __ldcg(partials + (long long)(k0 + u) * stride) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) b += v[u];
+    }
+    return b;
+}
+
+// SUM = false: only detect the last block (the caller sums the partials its own way).
+template <int NT, int NV, bool SUM = true>
 __device__ __forceinline__ bool grid_reduce_multi(const float (&v)[NV], double* partials, unsigned* ticket,
                                                   double* tot /* smem [NV] */, float* wsm /* smem [NT/32][NV] */,
                                                   int nblocks, int block_linear) {
@@ -75,10 +90,24 @@ __device__ __forceinline__ bool grid_reduce_multi(const float (&v)[NV], double* 
     __syncthreads();
     if (!s_last) return false;
     __threadfence();
-    for (int i = threadIdx.x; i < NV; i += NT) {
-        double b = 0.0;
-        for (int blk = 0; blk < nblocks; blk++) b += __ldcg(partials + (long long)blk * NV + i);
-        tot[i] = b;
+    if (SUM) {
+        // every value by PARTS threads, each over a contiguous share of the blocks, the shares added in order: a fixed
+        // order (deterministic), PARTS times shorter than one thread per value
+        constexpr int PARTS = (NV * 4 <= NT) ? 4 : ((NV * 2 <= NT) ? 2 : 1);
+        __shared__ double part_sm[NT];
+        const int per = (nblocks + PARTS - 1) / PARTS;
+        if (threadIdx.x < NV * PARTS) {
+            const int i = threadIdx.x / PARTS, q = threadIdx.x % PARTS;
+            const int b0 = q * per, cnt = max(0, min(per, nblocks - b0));
+            part_sm[threadIdx.x] = ordered_sum(partials + (long long)b0 * NV + i, cnt, NV);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < NV; i += NT) {
+            double b = 0.0;
+#pragma unroll
+            for (int q = 0; q < PARTS; q++) b += part_sm[i * PARTS + q];
+            tot[i] = b;
+        }
     }
     if (threadIdx.x == 0) *ticket = 0u;
     __syncthreads();
@@ -234,17 +263,14 @@ __global__ void __launch_bounds__(ST_NT, SRPS_LIGHT_MINB) lighting_reduce_kernel
     }
     const int nblocks = gridDim.x * gridDim.y;
     const int lin = blockIdx.y * gridDim.x + blockIdx.x;
-    if (!grid_reduce_multi<ST_NT, LIGHT_IB * 12>(acc, a.partials, a.ticket, tot, wsm, nblocks, lin)) return;
-    // ---- last block: `tot` holds the sum over ALL blocks of all groups (values of different groups
-    // were added together), so redo the per-group sums from the partials, then solve.
+    if (!grid_reduce_multi<ST_NT, LIGHT_IB * 12, false>(acc, a.partials, a.ticket, tot, wsm, nblocks, lin)) return;
+    // ---- last block: the blocks of one image group hold the partials of its images: per-group sums, then solve.
     __shared__ double s_new[MAX_IMAGES * 12];
     const int gx = gridDim.x;
     for (int e = threadIdx.x; e < a.n_images * 12; e += ST_NT) {
         const int img = e / 12, ck = e % 12;
         const int grp = img / LIGHT_IB, ii = img % LIGHT_IB;
-        double b = 0.0;
-        for (int bx = 0; bx < gx; bx++) b += __ldcg(a.partials + ((long long)(grp * gx + bx)) * (LIGHT_IB * 12) + ii * 12 + ck);
-        s_new[e] = b;                 // Atb for (img, c = ck/4, k = ck%4)
+        s_new[e] = ordered_sum(a.partials + (long long)grp * gx * (LIGHT_IB * 12) + ii * 12 + ck, gx, LIGHT_IB * 12);   // Atb for (img, c = ck/4, k = ck%4)
     }
     __syncthreads();
     peer_allreduce<ST_NT>(a.comm, s_new, a.n_images * 12);   // strip partition: sum over the ranks

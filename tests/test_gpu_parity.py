@@ -211,7 +211,10 @@ def test_each_iteration_from_synchronised_state(cfg, albedo_mode, stencil, monke
         assert np.abs(ctx.download("N") - stp["N"]).max() < 5e-6
         e_ref, k_ref, _ = pt.outer_iteration(stp, albedo_closed_form=(albedo_mode == "closed_form"))
         e_gpu, k_gpu = ctx.outer_iteration()
-        assert k_gpu == k_ref          # 101 unless r.r <= 1e-18 is reached (sf = 1: KtK = I, the CG can converge early)
+        # 101 unless r.r <= 1e-18 is reached (sf = 1, or a small well-conditioned scene: the CG converges early).  A full
+        # solve must give the identical count; WHERE a converging fp32 residual crosses 1e-18 depends on the last bits of
+        # the dot products, so an early stop may shift by a pass or two (the depth parity below is what matters there)
+        assert k_gpu == k_ref if k_ref == 101 else abs(k_gpu - k_ref) <= 2, (k_gpu, k_ref)
         assert rel_rmse(ctx.download("z"), stp["z"]) <= (1e-4 if loose else 2e-5), it
         assert np.abs(ctx.download("rho") - stp["rho"]).max() <= 3e-4, it
         assert shading_diff(ctx.download("s"), stp["s"], stp["N"]) <= 2e-3, it
