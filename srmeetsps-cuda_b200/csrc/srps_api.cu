@@ -65,12 +65,16 @@ struct srps_ctx {
     void* staging = nullptr; size_t staging_bytes = 0;
     // pinned host mirrors
     double* h_energy = nullptr; CgScalars* h_sc = nullptr;
+    struct HistSlot { double energy[2]; CgScalars sc; };   // what the host reads back per outer iteration
+    HistSlot* h_hist = nullptr;                            // pinned ring (HIST slots): srps_run(fixed_iters) queues whole
+                                                           // iterations without a host round trip and reads these at the end
     // launch geometry
     int grid_stencil = 0, grid_update = 0, grid_stack = 0, grid_light_x = 0, light_groups = 0, grid_ep = 0, grid_al = 0, grid_gram = 0;
     int tiles_x = 0, tiles_y = 0;
     int use_strip = 0, strip_n = 0, strip_chunks = 0, strip_cl = 0, grid_strip = 0;
     int use_persistent = 0, grid_persistent = 0;      // all CG passes in one cooperative launch
     int use_persistent_fused = 0;                     // ... in the fused form (one grid barrier per pass; opt-in)
+    int pf_minb = 3;                                  // CTAs per SM the persistent fused kernel is compiled for (SRPS_PF_MINB)
     int use_fused = 0;                                // one kernel per CG pass (cg_fused_kernel)
     int use_tma = 0;                                  // ... with the TMA-fed shared-memory ring (cg_fused_tma_kernel) for passes >= 1
     int lc_slot = -1;                                 // this context's slot of the constant-bank lighting constants (c_lc)
@@ -89,6 +93,8 @@ struct srps_ctx {
     int peer_ny[MAX_RANKS]{};
     long long peer_plane[MAX_RANKS]{};
 };
+
+constexpr int HIST = 32;      // outer iterations srps_run(fixed_iters) keeps in flight before it synchronises
 
 struct DistBlob {
     cudaIpcMemHandle_t planes, mbox;
@@ -133,6 +139,7 @@ static int fail(srps_ctx* ctx, int code, const std::string& msg) {
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 static HaloPeers halo_peers(const srps_ctx* ctx, const float* local_plane);
+static int iteration_timings(srps_ctx* ctx);
 static int halo_push(srps_ctx* ctx, std::initializer_list<const float*> planes);
 
 extern "C" const char* srps_build_info(void) { return "srps-b200 sm_100a " __DATE__ " " __TIME__; }
@@ -163,7 +170,7 @@ extern "C" void srps_ctx_destroy(srps_ctx* ctx) {
     cudaFree(ctx->plane_base); cudaFree(ctx->types_base); cudaFree(ctx->lrmask); cudaFree(ctx->idx); cudaFree(ctx->idx_lr);
     cudaFree(ctx->I_base); cudaFree(ctx->I8_base); cudaFree(ctx->z0lr); cudaFree(ctx->s); cudaFree(ctx->gram); cudaFree(ctx->lc); cudaFree(ctx->sc);
     cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->energy); cudaFree(ctx->staging); cudaFree(ctx->U);
-    cudaFreeHost(ctx->h_energy); cudaFreeHost(ctx->h_sc);
+    cudaFreeHost(ctx->h_energy); cudaFreeHost(ctx->h_sc); cudaFreeHost(ctx->h_hist);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     lc_slot_release(ctx->lc_slot);
@@ -194,11 +201,14 @@ static const void* fn_fused_tma(int sf, bool world) {
 static const void* fn_persistent(int sf) {
     return sf == 1 ? (const void*)cg_persistent_kernel<1> : (sf == 2 ? (const void*)cg_persistent_kernel<2> : (const void*)cg_persistent_kernel<4>);
 }
-static const void* fn_persistent_fused(int sf, bool world) {
-    if (world) return sf == 1 ? (const void*)cg_persistent_fused_kernel<1, 2> : (sf == 2 ? (const void*)cg_persistent_fused_kernel<2, 2>
-                                                                                           : (const void*)cg_persistent_fused_kernel<4, 2>);
-    return sf == 1 ? (const void*)cg_persistent_fused_kernel<1, 1> : (sf == 2 ? (const void*)cg_persistent_fused_kernel<2, 1>
-                                                                              : (const void*)cg_persistent_fused_kernel<4, 1>);
+template <int COH, int MINB>
+static const void* fn_persistent_fused_t(int sf) {
+    return sf == 1 ? (const void*)cg_persistent_fused_kernel<1, COH, MINB> : (sf == 2 ? (const void*)cg_persistent_fused_kernel<2, COH, MINB>
+                                                                                      : (const void*)cg_persistent_fused_kernel<4, COH, MINB>);
+}
+static const void* fn_persistent_fused(int sf, bool world, int minb = 3) {
+    if (minb == 4) return world ? fn_persistent_fused_t<2, 4>(sf) : fn_persistent_fused_t<1, 4>(sf);
+    return world ? fn_persistent_fused_t<2, 3>(sf) : fn_persistent_fused_t<1, 3>(sf);
 }
 static int occupancy(const void* fn, int threads) {
     int occ = 0;
@@ -344,6 +354,7 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     CK(cudaMalloc(&ctx->energy, sizeof(double) * 2));
     CK(cudaMallocHost(&ctx->h_energy, sizeof(double) * 2));
     CK(cudaMallocHost(&ctx->h_sc, sizeof(CgScalars) * 4));
+    CK(cudaMallocHost(&ctx->h_hist, sizeof(srps_ctx::HistSlot) * HIST));
     {
         CgScalars init[4];
         memset(init, 0, sizeof init);
@@ -385,7 +396,9 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
             ctx->use_persistent = occ_p > 0;
         }
         if (want_pf && ctx->use_strip && coop) {
-            occ_p = occupancy(fn_persistent_fused(sfk, ctx->world > 1), SW_NT);
+            const char* mb = getenv("SRPS_PF_MINB");
+            ctx->pf_minb = (mb && mb[0] == '4') ? 4 : 3;
+            occ_p = occupancy(fn_persistent_fused(sfk, ctx->world > 1, ctx->pf_minb), SW_NT);
             ctx->use_persistent_fused = ctx->use_persistent = occ_p > 0;
         }
         ctx->use_fused = ctx->use_strip && !ctx->use_persistent && !(cgm && strcmp(cgm, "graph") == 0);
@@ -401,7 +414,8 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         // (the <sf> instances, not a representative: a cooperative grid sized by another instance's occupancy could
         //  exceed what is resident at once)
         occ = std::max(1, std::min({occupancy(fn_strip_iter(sfk), SW_NT), occupancy(fn_fused(sfk, false, ctx->world > 1), SW_NT),
-                                    occupancy(fn_fused(sfk, true, ctx->world > 1), SW_NT), ctx->use_persistent ? occ_p : 1 << 20}));
+                                    occupancy(fn_fused(sfk, true, ctx->world > 1), SW_NT)}));
+        if (ctx->use_persistent) occ = ctx->use_persistent_fused ? occ_p : std::min(occ, occ_p);   // the solve is one launch of that kernel
         if (ctx->use_tma) occ = std::min(occ, occ_tma);    // the ring kernel is shared-memory bound: 2 CTAs per SM
         const int warps = ctx->sm_count * occ * (SW_NT / 32);
         // one (strip, chunk) item per resident warp: as many chunks per strip as the warps allow, then the chunk length
@@ -904,8 +918,9 @@ static int launch_cg_fused(srps_ctx* ctx, StencilArgs sa, int passes) {
     return 0;
 }
 
-extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
-    if (!ctx) return SRPS_E_INVALID;
+// Everything of the depth update is enqueued on the context's stream; the energy terms and the CG scalars are copied to
+// the pinned history slot `slot` (no host synchronisation here).
+static int depth_enqueue(srps_ctx* ctx, int slot) {
     if (!ctx->have_state) return fail(ctx, SRPS_E_STATE, "no state uploaded");
     CK(cudaSetDevice(ctx->device));
     const bool refcg = ctx->prob.albedo_mode == SRPS_ALBEDO_REFERENCE_CG;
@@ -949,7 +964,7 @@ extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
         peer_boundary_lines(ctx, ctx->y2, pa.y_prev[1], pa.y_next[1]);
         CK(cudaMemsetAsync(ctx->sync_words, 0, 2 * sizeof(unsigned long long), ctx->stream));
         void* kargs[] = {&pa};
-        const void* fn = ctx->use_persistent_fused ? fn_persistent_fused(ctx->g.sf, ctx->world > 1) : fn_persistent(ctx->g.sf);
+        const void* fn = ctx->use_persistent_fused ? fn_persistent_fused(ctx->g.sf, ctx->world > 1, ctx->pf_minb) : fn_persistent(ctx->g.sf);
         CK(cudaLaunchCooperativeKernel(fn, dim3(ctx->grid_persistent), dim3(SW_NT), kargs, 0, ctx->stream));
         ctx->launches++;
     } else if (getenv("SRPS_TRACE")) {
@@ -1000,16 +1015,31 @@ extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
     LAUNCH(ctx, energy_depth_kernel, (int)std::min<long long>((ncell + EP_NT - 1) / EP_NT, ctx->sm_count * 4), EP_NT, ea);
     CK(cudaGetLastError());
     ctx->pending_normals = true;
-    CK(cudaMemcpyAsync(ctx->h_energy, ctx->energy, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_sc, ctx->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->tm.cg_iters = ctx->h_sc[0].k;
-    ctx->tm.cg_deferred = ctx->h_sc[0].n_defer;
+    CK(cudaMemcpyAsync(ctx->h_hist[slot].energy, ctx->energy, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&ctx->h_hist[slot].sc, ctx->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+
+// After a stream synchronisation: what history slot `slot` says about its depth update
+static void depth_collect(srps_ctx* ctx, int slot, float* energy, int* cg_iters) {
+    const srps_ctx::HistSlot& hs = ctx->h_hist[slot];
+    ctx->h_sc[0] = hs.sc;
+    ctx->h_energy[0] = hs.energy[0]; ctx->h_energy[1] = hs.energy[1];
+    ctx->tm.cg_iters = hs.sc.k;
+    ctx->tm.cg_deferred = hs.sc.n_defer;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
     ctx->tm.ms_depth_cg = ms;
-    if (energy) *energy = (float)(ctx->h_energy[1] + ctx->h_energy[0]);     // t1 + lambda*t2, lambda = 1   devicecalls.cu:785
-    if (cg_iters) *cg_iters = ctx->h_sc[0].k;
+    if (energy) *energy = (float)(hs.energy[1] + hs.energy[0]);     // t1 + lambda*t2, lambda = 1   devicecalls.cu:785
+    if (cg_iters) *cg_iters = hs.sc.k;
+}
+
+extern "C" int srps_depth(srps_ctx* ctx, float* energy, int* cg_iters) {
+    if (!ctx) return SRPS_E_INVALID;
+    int rc;
+    if ((rc = depth_enqueue(ctx, 0))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    depth_collect(ctx, 0, energy, cg_iters);
     return 0;
 }
 
@@ -1023,8 +1053,8 @@ extern "C" int srps_normals(srps_ctx* ctx) {
     return launch_normals(ctx, false, ctx->N, ctx->dz);
 }
 
-extern "C" int srps_outer_iteration(srps_ctx* ctx, float* energy, int* cg_iters) {
-    if (!ctx) return SRPS_E_INVALID;
+// One pass of the loop body, enqueued only (SRPS.cu:276-317): the host does not wait for the device
+static int iteration_enqueue(srps_ctx* ctx, int slot) {
     int rc;
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -1032,11 +1062,23 @@ extern "C" int srps_outer_iteration(srps_ctx* ctx, float* energy, int* cg_iters)
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     if ((rc = srps_albedo(ctx))) return rc;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    if ((rc = srps_depth(ctx, energy, cg_iters))) return rc;
+    if ((rc = depth_enqueue(ctx, slot))) return rc;
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     if ((rc = srps_normals(ctx))) return rc;
     CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+    return 0;
+}
+
+extern "C" int srps_outer_iteration(srps_ctx* ctx, float* energy, int* cg_iters) {
+    if (!ctx) return SRPS_E_INVALID;
+    int rc;
+    if ((rc = iteration_enqueue(ctx, 0))) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
+    depth_collect(ctx, 0, energy, cg_iters);
+    return iteration_timings(ctx);
+}
+
+static int iteration_timings(srps_ctx* ctx) {
     cudaEventElapsedTime(&ctx->tm.ms_lighting, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->tm.ms_albedo, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&ctx->tm.ms_depth, ctx->ev[2], ctx->ev[3]);
@@ -1050,6 +1092,26 @@ extern "C" int srps_run(srps_ctx* ctx, int max_outer, float tol, int fixed_iters
     if (!ctx) return SRPS_E_INVALID;
     if (max_outer <= 0) max_outer = 10;      // SRPS.cu:86
     if (tol <= 0.f) tol = 5e-3f;             // SRPS.cu:85
+    if (fixed_iters > 0 && ctx->prob.albedo_mode == SRPS_ALBEDO_CLOSED_FORM && !getenv("SRPS_TRACE")) {
+        // A fixed number of passes needs no decision on the host: whole iterations are queued back to back (the device
+        // never waits for a launch, and the ranks of a strip partition stay in lock-step through their in-kernel
+        // collectives instead of re-aligning after every host round trip); the energies are read at the end.
+        int done = 0;
+        while (done < fixed_iters) {
+            const int batch = std::min(HIST, fixed_iters - done);
+            int rc;
+            for (int i = 0; i < batch; i++) if ((rc = iteration_enqueue(ctx, i))) return rc;
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (int i = 0; i < batch; i++) {
+                float e = 0.f;
+                depth_collect(ctx, i, &e, nullptr);
+                if (energies && done + i < cap) energies[done + i] = e;
+            }
+            done += batch;
+        }
+        if (n_done) *n_done = done;
+        return iteration_timings(ctx);       // per-phase times of the last pass
+    }
     float last = NAN;
     int iteration = 1;
     bool stop = false;

@@ -1093,8 +1093,11 @@ __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double 
     __syncthreads();
 }
 
-template <int SF, int COH>
-__global__ void __launch_bounds__(SW_NT, SRPS_FUSED_MINB) cg_persistent_fused_kernel(const PersistentArgs a) {
+// MINB: resident CTAs per SM the register allocation aims at.  3 (168 registers) is the bandwidth-optimal point of the
+// fused pass; 4 (128 registers, some spills) puts a third more warps on an SM, which shortens the chunk a warp walks --
+// measured as an option for strips / scenes of ~2 M pixels per GPU, where a pass is a handful of dependent round trips.
+template <int SF, int COH, int MINB = SRPS_FUSED_MINB>
+__global__ void __launch_bounds__(SW_NT, MINB) cg_persistent_fused_kernel(const PersistentArgs a) {
     static_assert(SW_NT / 32 == 4, "one warp per dot in grid_allreduce4");
     static_assert(COH == 1 || COH == 2, "1: single GPU, 2: strip partition (planes are rewritten inside this launch: coherent loads)");
     constexpr bool WORLD = (COH == 2);
