@@ -1021,7 +1021,6 @@ __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double 
                                                 double* wsm /* [SW_NT/32][4] */, double* s_tot /* [4] */, unsigned long long seq) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     __shared__ int s_islast;
-    __shared__ unsigned s_half[8];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const double s = warp_sum(v[i]);
@@ -1053,38 +1052,46 @@ __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double 
         if (lane == 0) s_tot[wid] = t;
         __syncthreads();
     } else {
-        // The last block to arrive sums the partials, exchanges the four rank totals with the peers and broadcasts the
-        // world totals to the other blocks of this GPU as eight self-validating words {tag | half a double} (one store
-        // each, no flag + fence + data round trip); everybody else polls those eight words with one 64-byte request.
+        // The last block to arrive sums the partials and stores this rank's four totals, as self-validating words
+        // {sequence tag | half a double}, into the mailbox of EVERY rank, its own included (one NVLink store per peer
+        // and word).  Every block of every rank then polls its own GPU's mailbox for the words of all ranks and forms the
+        // rank-ordered sum itself: bit-identical totals everywhere, no second hop from an exchanging block to the others.
+        const PeerComm& c = a.st.comm;
         const unsigned long long tagw = (seq & 0xffffffffull) << 32;
-        unsigned long long* bc = reinterpret_cast<unsigned long long*>(a.world_tot);
+        const int slot = (int)(seq & (MB_SLOTS - 1));
+        const int t = threadIdx.x >> 3, w = threadIdx.x & 7;          // (rank, word): 8 words = 4 doubles per rank
+        const bool talker = t < c.world && threadIdx.x < MAX_RANKS * 8;
+        __shared__ unsigned s_word[MAX_RANKS][8];
         if (s_islast) {
             __threadfence();
-            const double t = warp_sum(lane_strided_sum(a.part[which], (int)gridDim.x, 4, wid, lane));
-            if (lane == 0) s_tot[wid] = t;
+            const double tt = warp_sum(lane_strided_sum(a.part[which], (int)gridDim.x, 4, wid, lane));
+            if (lane == 0) s_tot[wid] = tt;
             __syncthreads();
-            peer_allreduce_small<SW_NT, 4>(a.st.comm, s_tot, false, seq);      // ghost lines are LL words: pure scalar exchange
-            if (threadIdx.x < 8) {
-                const unsigned long long bits = (unsigned long long)__double_as_longlong(s_tot[threadIdx.x >> 1]);
-                st_relaxed_sys_u64(bc + threadIdx.x, tagw | ((threadIdx.x & 1) ? (bits >> 32) : (bits & 0xffffffffull)));
+            if (talker) {
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(s_tot[w >> 1]);
+                st_relaxed_sys_u64(&c.peer[t]->ll[slot][c.rank][w], tagw | ((w & 1) ? (bits >> 32) : (bits & 0xffffffffull)));
             }
-        } else {
-            if (threadIdx.x < 8) {
-                unsigned long long w;
-                unsigned spins = 0u;
-                do {
-                    w = ld_relaxed_sys_u64(bc + threadIdx.x);
-                    if (++spins > SPIN_LIMIT) __trap();
-                } while ((w & 0xffffffff00000000ull) != tagw);
-                s_half[threadIdx.x] = (unsigned)(w & 0xffffffffull);
-                // acquire: the other blocks' r / y / p of this pass (fenced before their arrival, which the broadcasting
-                // block observed) must be what the next pass reads -- this also drops this SM's stale L1 lines
-                __threadfence();
-            }
-            __syncthreads();
-            if (threadIdx.x < 4)
-                s_tot[threadIdx.x] = __longlong_as_double((long long)((unsigned long long)s_half[2 * threadIdx.x] |
-                                                                      ((unsigned long long)s_half[2 * threadIdx.x + 1] << 32)));
+            if (threadIdx.x == 0) *c.seq = seq;
+        }
+        if (talker) {
+            unsigned long long x;
+            unsigned spins = 0u;
+            do {
+                x = ld_relaxed_sys_u64(&c.local->ll[slot][t][w]);
+                if (++spins > SPIN_LIMIT) __trap();
+            } while ((x & 0xffffffff00000000ull) != tagw);
+            s_word[t][w] = (unsigned)(x & 0xffffffffull);
+            // acquire: the other blocks' r / y / p of this pass (fenced before their arrival, which the sending block
+            // observed) must be what the next pass reads -- this also drops this SM's stale L1 lines
+            __threadfence();
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double total = 0.0;
+            for (int r = 0; r < c.world; r++)                                   // rank order: identical bits on every rank
+                total += __longlong_as_double((long long)((unsigned long long)s_word[r][2 * threadIdx.x] |
+                                                          ((unsigned long long)s_word[r][2 * threadIdx.x + 1] << 32)));
+            s_tot[threadIdx.x] = total;
         }
         __syncthreads();
     }
@@ -1093,9 +1100,10 @@ __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double 
     __syncthreads();
 }
 
-// MINB: resident CTAs per SM the register allocation aims at.  3 (168 registers) is the bandwidth-optimal point of the
-// fused pass; 4 (128 registers, some spills) puts a third more warps on an SM, which shortens the chunk a warp walks --
-// measured as an option for strips / scenes of ~2 M pixels per GPU, where a pass is a handful of dependent round trips.
+// MINB: resident CTAs per SM the register allocation aims at.  3 (168 registers) is the point the fused pass runs at;
+// 4 (128 registers, 0.9 KB of spills per thread) puts a third more warps on an SM and shortens the chunk a warp walks,
+// but measured (round 2, SRPS_PF_MINB=4) 3.22 against 2.18 ms per outer iteration at 1080p and 3.57 against 2.73 ms on
+// a 2 M-pixel strip: rejected, kept as a switch for the record.
 template <int SF, int COH, int MINB = SRPS_FUSED_MINB>
 __global__ void __launch_bounds__(SW_NT, MINB) cg_persistent_fused_kernel(const PersistentArgs a) {
     static_assert(SW_NT / 32 == 4, "one warp per dot in grid_allreduce4");
