@@ -154,6 +154,18 @@ int  srps_profile_kernels(srps_ctx* ctx, int reps, float* out_ms);
 /* Test hook: y = (Kt K + G^T M G) p with the M of the current rho/dz/s (masked host vectors). */
 int  srps_apply_depth_operator(srps_ctx* ctx, const float* p_host, float* y_host);
 
+/* ---- device-pointer forms of the four operators: the seam of devicecalls.cuh:26-37 itself -------------------------
+ * The caller keeps the loop state on the device in the reference's masked layouts and passes raw device pointers, as
+ * SRPS.cu:276-317 does.  Operands are imported into the context (device-to-device), results written back in place:
+ * srps_dev_lighting updates d_s, srps_dev_albedo d_rho, srps_dev_depth d_z (and returns the energy), srps_dev_normals
+ * fills d_N[4][npix] and d_dz for the given d_z.  d_I is imported when first seen.  Call them in the reference's order
+ * (lighting, albedo, depth, normals); single GPU.  include/srps_devicecalls_adapter.h gives them the reference's names. */
+int  srps_dev_lighting(srps_ctx* ctx, float* d_s, const float* d_rho, const float* d_N, const float* d_I);
+int  srps_dev_albedo(srps_ctx* ctx, const float* d_s, float* d_rho, const float* d_N, const float* d_I);
+int  srps_dev_depth(srps_ctx* ctx, const float* d_s, const float* d_rho, const float* d_N, const float* d_I, const float* d_dz,
+                    const float* d_z0s, float* d_z, float* energy, int* cg_iters);
+int  srps_dev_normals(srps_ctx* ctx, const float* d_z, float* d_N, float* d_dz);
+
 /* ---- one-shot depth pre-processing on the device (the parallel steps of SRPS.cu:117-149; no context needed) ----------
  * srps_init_depth_mean: mean over `frames` low-resolution depth frames (z0: [frames][n_lr], any pixel order) divided by
  * the frame count, hole = 1 where any frame is 0 (devicecalls.cu:95-125).  The flagged pixels are then inpainted by the

@@ -58,6 +58,11 @@ EXPORTS = {
     "srps_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "srps_profile_kernels": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "srps_apply_depth_operator": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "srps_dev_lighting": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "srps_dev_albedo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "srps_dev_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "srps_dev_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "srps_init_depth_mean": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "srps_init_depth_smooth_upsample": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                                   C.c_void_p, C.c_void_p]),

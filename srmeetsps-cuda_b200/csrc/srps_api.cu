@@ -52,6 +52,7 @@ struct srps_ctx {
     float* I = nullptr; float* I_base = nullptr;
     unsigned char* I8 = nullptr; unsigned char* I8_base = nullptr;
     bool stack_u8 = false;
+    const float* dev_I_seen = nullptr;       // device-pointer operators: the caller's masked stack this context last imported
     float *z = nullptr, *r = nullptr, *p = nullptr, *p2 = nullptr, *y = nullptr, *e0 = nullptr, *dz = nullptr, *dz_new = nullptr;
     float *r2 = nullptr, *y2 = nullptr;     // second residual / A p planes of the fused CG pass (ping-pong)
     float *w[3]{}, *gq[3]{}, *N[3]{}, *N_new[3]{}, *rho[3]{};
@@ -1334,6 +1335,114 @@ extern "C" int srps_pixel_range(const srps_ctx* ctx, long long* p0, long long* p
     if (p1) *p1 = ctx->pix0 + ctx->npix;
     if (q0) *q0 = ctx->lr0;
     if (q1) *q1 = ctx->lr0 + ctx->npixs;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-pointer forms of the four operators: the seam of devicecalls.cuh:26-37 itself.  The caller keeps the reference's
+// loop state on the device in the reference's masked layouts (d_s[n][c][4], d_rho[c][npix], d_N[4][npix], d_I[n][c][npix],
+// d_z[npix], d_dz[npix], d_z0s[npixs]; SURVEY §8 buffer table) and passes raw device pointers, exactly as SRPS.cu:276-317
+// does; every call imports its operands into the context's dense planes (device-to-device scatter), runs the operator and
+// exports what the reference's function updates in place.  include/srps_devicecalls_adapter.h wraps these in the
+// reference's own names and signatures.  All pointers must belong to the context's device.
+// ------------------------------------------------------------------------------------------------
+static int import_masked(srps_ctx* ctx, const float* d_src, float* dense_plane, int count, const int* idx) {
+    LAUNCH(ctx, scatter_kernel, (count + 255) / 256, 256, d_src, idx, dense_plane, count);
+    CK(cudaGetLastError());
+    return 0;
+}
+static int export_masked(srps_ctx* ctx, const float* dense_plane, float* d_dst, int count, const int* idx) {
+    LAUNCH(ctx, gather_kernel, (count + 255) / 256, 256, dense_plane, idx, d_dst, count);
+    CK(cudaGetLastError());
+    return 0;
+}
+static int import_common(srps_ctx* ctx, const float* d_s, const float* d_rho, const float* d_N, const float* d_I) {
+    int rc;
+    if (d_I && d_I != ctx->dev_I_seen) {          // the stack is constant over a run: imported when first seen (or replaced)
+        if ((rc = ensure_stack(ctx, false))) return rc;
+        for (int pl = 0; pl < ctx->n * 3; pl++)
+            if ((rc = import_masked(ctx, d_I + (size_t)pl * ctx->npix, ctx->I + (long long)pl * ctx->g.plane, ctx->npix, ctx->idx))) return rc;
+        ctx->dev_I_seen = d_I;
+        ctx->have_images = true;
+    }
+    if (!ctx->have_images) return fail(ctx, SRPS_E_STATE, "no image stack (pass d_I)");
+    if (d_s) {
+        CK(cudaMemcpyAsync(ctx->s, d_s, sizeof(float) * (size_t)ctx->n * 12, cudaMemcpyDeviceToDevice, ctx->stream));
+        LAUNCH(ctx, light_consts_kernel, 1, 32, ctx->s, ctx->n, ctx->lc);
+        CK(cudaGetLastError());
+        if ((rc = publish_lc(ctx))) return rc;
+    }
+    if (d_rho) for (int c = 0; c < 3; c++) if ((rc = import_masked(ctx, d_rho + (size_t)c * ctx->npix, ctx->rho[c], ctx->npix, ctx->idx))) return rc;
+    if (d_N) {
+        apply_pending_normals(ctx);
+        for (int c = 0; c < 3; c++) if ((rc = import_masked(ctx, d_N + (size_t)c * ctx->npix, ctx->N[c], ctx->npix, ctx->idx))) return rc;
+    }
+    ctx->have_state = true;
+    return 0;
+}
+
+extern "C" int srps_dev_lighting(srps_ctx* ctx, float* d_s, const float* d_rho, const float* d_N, const float* d_I) {
+    if (!ctx || !d_s || !d_rho || !d_N) return fail(ctx, SRPS_E_INVALID, "null argument");
+    if (ctx->world > 1) return fail(ctx, SRPS_E_INVALID, "device-pointer operators are single-GPU (as the reference is)");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = import_common(ctx, d_s, d_rho, d_N, d_I))) return rc;       // d_s: warm start (devicecalls.cu:424)
+    if ((rc = srps_lighting(ctx))) return rc;
+    CK(cudaMemcpyAsync(d_s, ctx->s, sizeof(float) * (size_t)ctx->n * 12, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int srps_dev_albedo(srps_ctx* ctx, const float* d_s, float* d_rho, const float* d_N, const float* d_I) {
+    if (!ctx || !d_s || !d_rho || !d_N) return fail(ctx, SRPS_E_INVALID, "null argument");
+    if (ctx->world > 1) return fail(ctx, SRPS_E_INVALID, "device-pointer operators are single-GPU (as the reference is)");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = import_common(ctx, d_s, d_rho, d_N, d_I))) return rc;       // d_rho: warm start of the diagonal CG (devicecalls.cu:540)
+    if ((rc = srps_albedo(ctx))) return rc;
+    for (int c = 0; c < 3; c++) if ((rc = export_masked(ctx, ctx->rho[c], d_rho + (size_t)c * ctx->npix, ctx->npix, ctx->idx))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int srps_dev_depth(srps_ctx* ctx, const float* d_s, const float* d_rho, const float* d_N, const float* d_I, const float* d_dz,
+                              const float* d_z0s, float* d_z, float* energy, int* cg_iters) {
+    if (!ctx || !d_s || !d_rho || !d_N || !d_dz || !d_z0s || !d_z) return fail(ctx, SRPS_E_INVALID, "null argument");
+    if (ctx->world > 1) return fail(ctx, SRPS_E_INVALID, "device-pointer operators are single-GPU (as the reference is)");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    // The depth coefficients depend on s, rho, N, dz of THIS call.  In reference-CG mode they are formed inside srps_depth
+    // from the stack projection U of the preceding srps_albedo (same s: the reference's order, SRPS.cu:287-293); in
+    // closed-form mode the albedo pass formed them already with its own rho.
+    if (ctx->prob.albedo_mode == SRPS_ALBEDO_REFERENCE_CG) {
+        if ((rc = import_common(ctx, nullptr, d_rho, nullptr, d_I))) return rc;
+        if ((rc = import_masked(ctx, d_dz, ctx->dz, ctx->npix, ctx->idx))) return rc;
+        ctx->coeffs_valid = false;
+    }
+    if ((rc = import_masked(ctx, d_z, ctx->z, ctx->npix, ctx->idx))) return rc;
+    if (ctx->npixs > 0 && (rc = import_masked(ctx, d_z0s, ctx->z0lr, ctx->npixs, ctx->idx_lr))) return rc;
+    if ((rc = srps_depth(ctx, energy, cg_iters))) return rc;
+    if ((rc = export_masked(ctx, ctx->z, d_z, ctx->npix, ctx->idx))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    (void)d_s; (void)d_N;
+    return 0;
+}
+
+extern "C" int srps_dev_normals(srps_ctx* ctx, const float* d_z, float* d_N, float* d_dz) {
+    if (!ctx || !d_z || !d_N || !d_dz) return fail(ctx, SRPS_E_INVALID, "null argument");
+    if (ctx->world > 1) return fail(ctx, SRPS_E_INVALID, "device-pointer operators are single-GPU (as the reference is)");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    ctx->pending_normals = false;
+    if ((rc = import_masked(ctx, d_z, ctx->z, ctx->npix, ctx->idx))) return rc;
+    if ((rc = launch_normals(ctx, false, ctx->N, ctx->dz))) return rc;
+    for (int c = 0; c < 3; c++) if ((rc = export_masked(ctx, ctx->N[c], d_N + (size_t)c * ctx->npix, ctx->npix, ctx->idx))) return rc;
+    LAUNCH(ctx, fill_linear_kernel, (ctx->npix + 255) / 256, 256, d_N + (size_t)3 * ctx->npix, ctx->npix, 1.f);      // N[3] = 1  devicecalls.cu:175
+    if ((rc = export_masked(ctx, ctx->dz, d_dz, ctx->npix, ctx->idx))) return rc;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_state = true;
+    ctx->coeffs_valid = false;
     return 0;
 }
 

@@ -155,6 +155,10 @@ __global__ void gather_kernel(const float* __restrict__ src, const int* __restri
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[idx[i]];
 }
+__global__ void fill_linear_kernel(float* __restrict__ dst, int n, float v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = v;
+}
 __global__ void fill_masked_kernel(const int* __restrict__ idx, float* __restrict__ dst, int n, float v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[idx[i]] = v;                              // rho = 0.5   devicecalls.cu:133-139
