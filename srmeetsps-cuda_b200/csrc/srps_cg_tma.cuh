@@ -103,11 +103,8 @@ __device__ __forceinline__ double strip_pass_tma(const StencilArgs& a, const Lig
         auto load_ghost = [&](int side, int j, float4& rn, float4& pin, float& ypn) -> float4 {
             const bool ok = colok && x >= 0;
             float4 r4 = f4zero(), y4 = f4zero();
-            if (ok) {
-                r4 = ll_load4(a.ll.in + a.ll.at(tag_in, side, 0), x, tag_in);
-                y4 = ll_load4(a.ll.in + a.ll.at(tag_in, side, 1), x, tag_in);
-            }
-            pin = ldg4(a.p_in + (ok ? (long long)j * pitch + x : 0));
+            pin = ldg4(a.p_in + (ok ? (long long)j * pitch + x : 0));                          // independent of the LL words: issued first
+            if (ok) ll_load4x2(a.ll.in + a.ll.at(tag_in, side, 0), a.ll.in + a.ll.at(tag_in, side, 1), x, tag_in, r4, y4);
             rn = make_float4(r4.x - alpha * y4.x, r4.y - alpha * y4.y, r4.z - alpha * y4.z, r4.w - alpha * y4.w);
             const float4 pn = make_float4(rn.x + beta * pin.x, rn.y + beta * pin.y, rn.z + beta * pin.z, rn.w + beta * pin.w);
             ypn = (y4.x * pn.x + y4.y * pn.y) + (y4.z * pn.z + y4.w * pn.w);

@@ -249,6 +249,27 @@ __device__ __forceinline__ float4 ll_load4(const unsigned long long* line, int x
                        __uint_as_float((unsigned)w3));
 }
 
+// two lines (r and y of the same ghost line) at once: all four 16-byte loads are in flight together, one round trip to L2
+// instead of two on the critical path of the strip's first / last chunk
+__device__ __forceinline__ void ll_load4x2(const unsigned long long* line_a, const unsigned long long* line_b, int x, unsigned tag,
+                                           float4& a, float4& b) {
+    unsigned long long w[8];
+    unsigned spins = 0u;
+    bool ok;
+    do {
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(line_a + x) : "memory");
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[2]), "=l"(w[3]) : "l"(line_a + x + 2) : "memory");
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[4]), "=l"(w[5]) : "l"(line_b + x) : "memory");
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[6]), "=l"(w[7]) : "l"(line_b + x + 2) : "memory");
+        ok = true;
+#pragma unroll
+        for (int i = 0; i < 8; i++) ok = ok && ((unsigned)(w[i] >> 32) == tag);
+        if (++spins > SPIN_LIMIT) __trap();
+    } while (!ok);
+    a = make_float4(__uint_as_float((unsigned)w[0]), __uint_as_float((unsigned)w[1]), __uint_as_float((unsigned)w[2]), __uint_as_float((unsigned)w[3]));
+    b = make_float4(__uint_as_float((unsigned)w[4]), __uint_as_float((unsigned)w[5]), __uint_as_float((unsigned)w[6]), __uint_as_float((unsigned)w[7]));
+}
+
 // Ghost-line destinations in the neighbours' planes (mapped peer pointers), per plane kind.
 struct HaloPeers {
     float* prev_ghost;     // address of the previous rank's ghost line `ny_prev` of this plane, or nullptr
