@@ -28,7 +28,7 @@ if os.path.exists(path):
         a = agg.setdefault(r[idx["Kernel Name"]], [0, 0.0])
         a[0] += 1
         a[1] += v
-    ours = {k: v for k, v in agg.items() if "srps::" in k or "light_consts" in k or "cg_" in k or "stencil" in k or "lighting" in k}
+    ours = {k: v for k, v in agg.items() if "at::" not in k and "elementwise" not in k}      # (capture.sh already filters on the library's kernel names)
     tot = sum(v[1] for v in ours.values())
     out = [f"# ncu --metrics gpu__time_duration.sum --clock-control none (first launches of the library's kernels)  python bench.py --steps 2 --warmup 1 --no-cpu   (SRPS_NO_GRAPH=1)",
            "# 4096x4096 HR, sf=4, 32 images; cold-cache serialised launch times: compare SHARES, not absolutes.",
