@@ -345,17 +345,40 @@ def strip_parity_check(rank, world, local, albedo):
     return out
 
 
-def time_workload(name, local, albedo, steps, warmup):
+def quantise_stack_u8(I, local):
+    """The synthetic fp32 stack as the 8-bit samples an image dataset would hold (round(255 I)), pinned host memory;
+    converted plane by plane on the GPU."""
+    import torch
+    I8 = torch.empty(I.shape, dtype=torch.uint8, pin_memory=True)
+    src = torch.from_numpy(I)
+    for i in range(I.shape[0]):
+        I8[i].copy_((src[i].to(f"cuda:{local}", non_blocking=True) * 255.0).round_().clamp_(0, 255).to(torch.uint8))
+    torch.cuda.synchronize()
+    return I8
+
+
+def time_workload(name, local, albedo, steps, warmup, stack="f32"):
     """One single-GPU workload timed the way the headline is (device-resident value, e2e from pinned host): the
-    same-size leg of the reference ratio and the config-3 line."""
+    same-size leg of the reference ratio, the config-3 line and the 8-bit-stack line (stack="u8": the images are
+    quantised to 8 bits and stay 8-bit in HBM, srps_upload_images_u8)."""
     import numpy as np
     import torch
     from srmeetsps_cuda_b200 import Context
     from srmeetsps_cuda_b200.synth import synth_scene_torch
     h, w, sf, n, seed = WORKLOADS[name]
     sc = synth_scene_torch(h, w, sf, n, seed, device=f"cuda:{local}")
+    I8t = quantise_stack_u8(sc["I"], local) if stack == "u8" else None
+    I8 = I8t.numpy() if I8t is not None else None
+
+    def upload(ctx):
+        if I8 is not None:
+            ctx.upload_images_u8(I8)
+            ctx.upload_state(None, sc["z"], sc["z0s"])
+        else:
+            ctx.upload_state(sc["I"], sc["z"], sc["z0s"])
+
     with Context(sc["mask"], n, sf, sc["K"], device=local, albedo_mode=albedo) as ctx:
-        ctx.upload_state(sc["I"], sc["z"], sc["z0s"])
+        upload(ctx)
         for _ in range(warmup):
             ctx.outer_iteration()
         ctx.timer_start()
@@ -370,16 +393,18 @@ def time_workload(name, local, albedo, steps, warmup):
         out = {k: torch.empty(s_, dtype=torch.float32, pin_memory=True).numpy() for k, s_ in
                (("z", (ctx.npix,)), ("rho", (3, ctx.npix)), ("N", (4, ctx.npix)), ("s", (n, 3, 4)))}
         ctx.timer_start()
-        ctx.upload_state(sc["I"], sc["z"], sc["z0s"])
+        upload(ctx)
         ctx.run(fixed_iters=steps)
         for k in out:
             ctx.download(k, out=out[k])
         e2e = ctx.timer_stop() / steps
+        phases = {key: float(t[key]) for key in ("ms_lighting", "ms_albedo", "ms_depth")}
+        h2d = (I8.nbytes if I8 is not None else sc["I"].nbytes) + sc["z"].nbytes + sc["z0s"].nbytes
     del sc
     torch.cuda.empty_cache()
     return {"workload": f"{h}x{w} HR, sf={sf}, {n} images, full mask", "value": float(ms_value), "unit": "ms",
             "per_separately_synchronised_iteration": float(np.mean(per)), "e2e": float(e2e), "steps": steps, "warmup": warmup,
-            "ms_depth_cg": float(np.mean(cg)), "cg_iters": int(cg_k)}
+            "ms_depth_cg": float(np.mean(cg)), "cg_iters": int(cg_k), "phases_ms": phases, "stack": stack, "h2d_bytes": float(h2d)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -506,6 +531,10 @@ def run_ours(args, rank, world, local):
         same_size["note"] = ("the reference CUDA build runs this size itself (bench.py --impl reference prints its un-scaled "
                              "measurement under the same key): a same-configuration pair for the speed-up")
         extra = {"config3_1080p": time_workload("1080p", local, args.albedo, steps=10, warmup=3)}
+        try:            # the headline workload with the 8-bit stack (N3): the fp32 line above stays the headline
+            extra["config4_u8_stack"] = time_workload("4k", local, args.albedo, steps=10, warmup=3, stack="u8")
+        except Exception as ex:
+            extra["config4_u8_stack"] = {"error": repr(ex)}
         try:
             extra["config5_batch_1gpu"] = batch_scenes(local, 1, 0, 4, args.albedo)
         except Exception as ex:                                     # never lose the headline line to an extra

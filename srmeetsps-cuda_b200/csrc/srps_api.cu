@@ -58,7 +58,7 @@ struct srps_ctx {
     float *w[3]{}, *gq[3]{}, *N[3]{}, *N_new[3]{}, *rho[3]{};
     float *U = nullptr, *ad[3]{}, *ar[3]{}, *ap[3]{};    // reference-CG albedo only
     float* z0lr = nullptr;
-    float* s = nullptr; float* gram = nullptr; LightConsts* lc = nullptr;
+    float* s = nullptr; double* gram = nullptr; LightConsts* lc = nullptr;
     CgScalars* sc = nullptr;       // [4]: depth, albedo c=0..2
     double* partials = nullptr; long long partials_len = 0;
     unsigned* tickets = nullptr;   // [8]
@@ -337,7 +337,7 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     CK(cudaMalloc(&ctx->z0lr, sizeof(float) * std::max<size_t>(lr_cells, 1)));
     CK(cudaMemsetAsync(ctx->z0lr, 0, sizeof(float) * std::max<size_t>(lr_cells, 1), ctx->stream));
     CK(cudaMalloc(&ctx->s, sizeof(float) * (size_t)ctx->n * 12));
-    CK(cudaMalloc(&ctx->gram, sizeof(float) * 48));
+    CK(cudaMalloc(&ctx->gram, sizeof(double) * 30));
     static_assert(LC_SLOTS <= 64, "slot bitmap is one 64-bit word");
     if ((ctx->lc_slot = lc_slot_acquire()) < 0) return fail(ctx, SRPS_E_INVALID, "more than 64 live contexts in this process");
     CK(cudaMalloc(&ctx->lc, sizeof(LightConsts)));

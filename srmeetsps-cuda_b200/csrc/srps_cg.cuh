@@ -923,7 +923,7 @@ __device__ __forceinline__ double grid_allreduce(const PersistentArgs& a, double
         if (peer_stores) __threadfence_system(); else __threadfence();
         atomicAdd(a.bar, 1ull);
         const unsigned long long target = (gen + 1ull) * gridDim.x;
-        while (ld_acquire_gpu(a.bar) < target) { }
+        while (ld_acquire_gpu(a.bar) < target) { poll_backoff(); }
     }
     __syncthreads();
     gen += 1ull;
@@ -1038,7 +1038,7 @@ __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double 
         if (WORLD) {
             s_islast = (t == target - 1ull);
         } else {
-            while (ld_acquire_gpu(a.bar) < target) { }
+            while (ld_acquire_gpu(a.bar) < target) { poll_backoff(); }
         }
     }
     __syncthreads();
@@ -1075,6 +1075,7 @@ __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double 
             unsigned spins = 0u;
             do {
                 x = ld_relaxed_sys_u64(&c.local->ll[slot][t][w]);
+                if ((x & 0xffffffff00000000ull) != tagw) poll_backoff();
                 if (++spins > SPIN_LIMIT) __trap();
             } while ((x & 0xffffffff00000000ull) != tagw);
             s_word[t][w] = (unsigned)(x & 0xffffffffull);

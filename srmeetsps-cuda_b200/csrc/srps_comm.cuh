@@ -20,9 +20,17 @@ namespace srps {
 
 constexpr int MAX_RANKS = 8;
 constexpr int MB_SLOTS = 4;
-constexpr int MB_VALS = 800;      // doubles per (slot, source rank): lighting needs n*12 <= 768
+constexpr int MB_VALS = 800;      // doubles per (slot, source rank): lighting needs n*12 + 30 <= 798
 constexpr int MB_SMALL = 4;       // doubles per (slot, source rank) on the latency-optimised path (fused CG pass: 4 dots)
 constexpr unsigned SPIN_LIMIT = 1u << 26;   // polls of one word before a waiting thread traps (tens of seconds)
+#ifndef SRPS_POLL_NS
+#define SRPS_POLL_NS 0           // pause between two polls of a barrier word (0: spin): hundreds of blocks poll the same L2 lines
+#endif
+__device__ __forceinline__ void poll_backoff() {
+#if SRPS_POLL_NS > 0
+    __nanosleep(SRPS_POLL_NS);
+#endif
+}
 
 struct Mailbox {
     unsigned long long flag[MB_SLOTS][MAX_RANKS];

@@ -123,7 +123,8 @@ struct GramArgs {
     long long n4;
     double* partials;      // [grid][30]
     unsigned* ticket;
-    float* gram;           // out: [3][16] full symmetric 4x4 per channel
+    double* gram;          // out: [30] this RANK's sums, upper triangles of the three 4x4 (the cross-rank sum happens together
+                           //      with the right-hand sides in lighting_reduce_kernel: one exchange per lighting update, not two)
     PeerComm comm;
 };
 
@@ -152,13 +153,7 @@ __global__ void __launch_bounds__(ST_NT, 4) lighting_gram_kernel(const GramArgs 
         }
     }
     if (grid_reduce_multi<ST_NT, 30>(acc, a.partials, a.ticket, tot, wsm, gridDim.x, blockIdx.x)) {
-        peer_allreduce<ST_NT>(a.comm, tot, 30);          // strip partition: sum over the ranks
-        if (threadIdx.x < 48) {
-            const int c = threadIdx.x / 16, e = threadIdx.x % 16, x = e / 4, y = e % 4;
-            const int lo = x < y ? x : y, hi = x < y ? y : x;
-            const int q = lo * 4 - (lo * (lo - 1)) / 2 + (hi - lo);     // index into the upper triangle
-            a.gram[c * 16 + e] = (float)tot[c * 10 + q];
-        }
+        if (threadIdx.x < 30) a.gram[threadIdx.x] = tot[threadIdx.x];
     }
 }
 
@@ -176,7 +171,7 @@ struct LightArgs {
     int n_images;
     double* partials;      // [gridDim.x*gridDim.y][96]
     unsigned* ticket;
-    const float* gram;     // [3][16]
+    const double* gram;    // [30] this rank's Gram sums (lighting_gram_kernel)
     float* s;              // in/out [n][3][4]
     LightConsts* lc;       // out
     int max_iter; float tol2;
@@ -265,19 +260,29 @@ __global__ void __launch_bounds__(ST_NT, SRPS_LIGHT_MINB) lighting_reduce_kernel
     const int lin = blockIdx.y * gridDim.x + blockIdx.x;
     if (!grid_reduce_multi<ST_NT, LIGHT_IB * 12, false>(acc, a.partials, a.ticket, tot, wsm, nblocks, lin)) return;
     // ---- last block: the blocks of one image group hold the partials of its images: per-group sums, then solve.
-    __shared__ double s_new[MAX_IMAGES * 12];
+    __shared__ double s_new[MAX_IMAGES * 12 + 30];
     const int gx = gridDim.x;
     for (int e = threadIdx.x; e < a.n_images * 12; e += ST_NT) {
         const int img = e / 12, ck = e % 12;
         const int grp = img / LIGHT_IB, ii = img % LIGHT_IB;
         s_new[e] = ordered_sum(a.partials + (long long)grp * gx * (LIGHT_IB * 12) + ii * 12 + ck, gx, LIGHT_IB * 12);   // Atb for (img, c = ck/4, k = ck%4)
     }
+    const int nrhs = a.n_images * 12;
+    for (int e = threadIdx.x; e < 30; e += ST_NT) s_new[nrhs + e] = a.gram[e];          // Gram sums ride along: one exchange
     __syncthreads();
-    peer_allreduce<ST_NT>(a.comm, s_new, a.n_images * 12);   // strip partition: sum over the ranks
+    peer_allreduce<ST_NT>(a.comm, s_new, nrhs + 30);         // strip partition: sum over the ranks
+    __shared__ float gram_sm[48];                            // the three full symmetric 4x4
+    if (threadIdx.x < 48) {
+        const int c = threadIdx.x / 16, e = threadIdx.x % 16, x = e / 4, y = e % 4;
+        const int lo = x < y ? x : y, hi = x < y ? y : x;
+        const int q = lo * 4 - (lo * (lo - 1)) / 2 + (hi - lo);     // index into the upper triangle
+        gram_sm[threadIdx.x] = (float)s_new[nrhs + c * 10 + q];
+    }
+    __syncthreads();
     for (int e = threadIdx.x; e < a.n_images * 3; e += ST_NT) {
         const int c = e % 3;
         float A[16], x[4], b[4];
-        for (int t = 0; t < 16; t++) A[t] = a.gram[c * 16 + t];
+        for (int t = 0; t < 16; t++) A[t] = gram_sm[c * 16 + t];
         for (int t = 0; t < 4; t++) x[t] = a.s[e * 4 + t];
         for (int t = 0; t < 4; t++) {                         // residual Atb - AtA s   devicecalls.cu:424
             float ax = 0.f;
