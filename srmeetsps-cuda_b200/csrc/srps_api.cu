@@ -76,6 +76,7 @@ struct srps_ctx {
     int use_persistent = 0, grid_persistent = 0;      // all CG passes in one cooperative launch
     int use_persistent_fused = 0;                     // ... in the fused form (one grid barrier per pass; opt-in)
     int pf_minb = 3;                                  // CTAs per SM the persistent fused kernel is compiled for (SRPS_PF_MINB)
+    int pf_nt = SW_NT;                                // its threads per CTA (SRPS_PF_NT=384: one fat CTA per SM)
     int use_fused = 0;                                // one kernel per CG pass (cg_fused_kernel)
     int use_tma = 0;                                  // ... with the TMA-fed shared-memory ring (cg_fused_tma_kernel) for passes >= 1
     int lc_slot = -1;                                 // this context's slot of the constant-bank lighting constants (c_lc)
@@ -202,14 +203,16 @@ static const void* fn_fused_tma(int sf, bool world) {
 static const void* fn_persistent(int sf) {
     return sf == 1 ? (const void*)cg_persistent_kernel<1> : (sf == 2 ? (const void*)cg_persistent_kernel<2> : (const void*)cg_persistent_kernel<4>);
 }
-template <int COH, int MINB>
+constexpr int PF_FAT_NT = 384;       // the twelve warps of an SM in one CTA (persistent fused kernel, SRPS_PF_NT=384)
+template <int COH, int MINB, int NT>
 static const void* fn_persistent_fused_t(int sf) {
-    return sf == 1 ? (const void*)cg_persistent_fused_kernel<1, COH, MINB> : (sf == 2 ? (const void*)cg_persistent_fused_kernel<2, COH, MINB>
-                                                                                      : (const void*)cg_persistent_fused_kernel<4, COH, MINB>);
+    return sf == 1 ? (const void*)cg_persistent_fused_kernel<1, COH, MINB, NT> : (sf == 2 ? (const void*)cg_persistent_fused_kernel<2, COH, MINB, NT>
+                                                                                          : (const void*)cg_persistent_fused_kernel<4, COH, MINB, NT>);
 }
-static const void* fn_persistent_fused(int sf, bool world, int minb = 3) {
-    if (minb == 4) return world ? fn_persistent_fused_t<2, 4>(sf) : fn_persistent_fused_t<1, 4>(sf);
-    return world ? fn_persistent_fused_t<2, 3>(sf) : fn_persistent_fused_t<1, 3>(sf);
+static const void* fn_persistent_fused(int sf, bool world, int minb = 3, int nt = SW_NT) {
+    if (nt == PF_FAT_NT) return world ? fn_persistent_fused_t<2, 1, PF_FAT_NT>(sf) : fn_persistent_fused_t<1, 1, PF_FAT_NT>(sf);
+    if (minb == 4) return world ? fn_persistent_fused_t<2, 4, SW_NT>(sf) : fn_persistent_fused_t<1, 4, SW_NT>(sf);
+    return world ? fn_persistent_fused_t<2, 3, SW_NT>(sf) : fn_persistent_fused_t<1, 3, SW_NT>(sf);
 }
 static int occupancy(const void* fn, int threads) {
     int occ = 0;
@@ -399,7 +402,9 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         if (want_pf && ctx->use_strip && coop) {
             const char* mb = getenv("SRPS_PF_MINB");
             ctx->pf_minb = (mb && mb[0] == '4') ? 4 : 3;
-            occ_p = occupancy(fn_persistent_fused(sfk, ctx->world > 1, ctx->pf_minb), SW_NT);
+            const char* nt = getenv("SRPS_PF_NT");
+            ctx->pf_nt = (nt && atoi(nt) == PF_FAT_NT) ? PF_FAT_NT : SW_NT;
+            occ_p = occupancy(fn_persistent_fused(sfk, ctx->world > 1, ctx->pf_minb, ctx->pf_nt), ctx->pf_nt) * (ctx->pf_nt / SW_NT);   // in 128-thread units
             ctx->use_persistent_fused = ctx->use_persistent = occ_p > 0;
         }
         ctx->use_fused = ctx->use_strip && !ctx->use_persistent && !(cgm && strcmp(cgm, "graph") == 0);
@@ -428,6 +433,10 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         const int nitems = ctx->strip_n * ctx->strip_chunks;
         ctx->grid_strip = std::min((nitems + SW_NT / 32 - 1) / (SW_NT / 32), ctx->sm_count * occ);
         ctx->grid_persistent = ctx->grid_strip;            // <= sm_count * occ_p: all blocks co-resident
+        if (ctx->use_persistent_fused && ctx->pf_nt != SW_NT) {
+            const int wpb = ctx->pf_nt / 32;
+            ctx->grid_persistent = std::min((nitems + wpb - 1) / wpb, ctx->sm_count * (occ * SW_NT / ctx->pf_nt));
+        }
         CK(cudaMalloc(&ctx->sync_words, 16 * sizeof(unsigned long long)));
         CK(cudaMemsetAsync(ctx->sync_words, 0, 16 * sizeof(unsigned long long), ctx->stream));
     }
@@ -965,8 +974,8 @@ static int depth_enqueue(srps_ctx* ctx, int slot) {
         peer_boundary_lines(ctx, ctx->y2, pa.y_prev[1], pa.y_next[1]);
         CK(cudaMemsetAsync(ctx->sync_words, 0, 2 * sizeof(unsigned long long), ctx->stream));
         void* kargs[] = {&pa};
-        const void* fn = ctx->use_persistent_fused ? fn_persistent_fused(ctx->g.sf, ctx->world > 1, ctx->pf_minb) : fn_persistent(ctx->g.sf);
-        CK(cudaLaunchCooperativeKernel(fn, dim3(ctx->grid_persistent), dim3(SW_NT), kargs, 0, ctx->stream));
+        const void* fn = ctx->use_persistent_fused ? fn_persistent_fused(ctx->g.sf, ctx->world > 1, ctx->pf_minb, ctx->pf_nt) : fn_persistent(ctx->g.sf);
+        CK(cudaLaunchCooperativeKernel(fn, dim3(ctx->grid_persistent), dim3(ctx->use_persistent_fused ? ctx->pf_nt : SW_NT), kargs, 0, ctx->stream));
         ctx->launches++;
     } else if (getenv("SRPS_TRACE")) {
         // debugging aid: one pass at a time, CG scalars printed after each (no graph)

@@ -382,7 +382,7 @@ __device__ __forceinline__ LineQ line_q(const LightConsts& lc, float fx, float f
 // tagged tag_in + 1, and -- MODE_FUSED -- the ghost lines of r and y_in are read from this rank's LL buffer (tag_in)
 // instead of being pulled from the neighbours' planes; MODE_FUSED0 (first pass of a solve) still pulls r, which the
 // residual kernel wrote and ordered with its system-scope reduction.
-template <int MODE, int SF, int COH = 0, bool LLG = false>
+template <int MODE, int SF, int COH = 0, bool LLG = false, int NT = SW_NT>
 __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightConsts& lc, float beta, float alpha = 0.f,
                                              double* extra = nullptr /* FUSED: r.r, y_in.p, y.y */, unsigned tag_in = 0u) {
     static_assert(MODE == MODE_ITER || MODE == MODE_APPLY || MODE == MODE_FUSED || MODE == MODE_FUSED0,
@@ -398,7 +398,7 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
     const int nitems = a.strip_n * a.strip_chunks;
     double dot = 0.0, s_rr = 0.0, s_yp = 0.0, s_yy = 0.0;
 
-    for (int item = blockIdx.x * (SW_NT / 32) + warp; item < nitems; item += gridDim.x * (SW_NT / 32)) {
+    for (int item = blockIdx.x * (NT / 32) + warp; item < nitems; item += gridDim.x * (NT / 32)) {
         const int strip = item % a.strip_n, chunk = item / a.strip_n;
         const int x = 4 * (strip * SW_COLS - 1 + lane);            // x = -4 on lane 0 of strip 0: the zero pad of the previous line
         const bool colok = x < pitch;
@@ -1013,9 +1013,9 @@ __global__ void __launch_bounds__(SW_NT, SRPS_STRIP_MINB) cg_persistent_kernel(c
 // word; everybody else spins on that word.  The ghost lines of r / y do not depend on this barrier: every pass pushes
 // its boundary lines to the neighbours as self-validating LL words (GhostLL, srps_comm.cuh).
 // ---------------------------------------------------------------------------------------------
-template <bool WORLD>
+template <bool WORLD, int NT>
 __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double (&v)[4], int which, unsigned long long& gen,
-                                                double* wsm /* [SW_NT/32][4] */, double* s_tot /* [4] */, unsigned long long seq) {
+                                                double* wsm /* [NT/32][4] */, double* s_tot /* [4] */, unsigned long long seq) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     __shared__ int s_islast;
 #pragma unroll
@@ -1027,7 +1027,7 @@ __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double 
     if (threadIdx.x < 4) {
         double b = 0.0;
 #pragma unroll
-        for (int w = 0; w < SW_NT / 32; w++) b += wsm[w * 4 + threadIdx.x];
+        for (int w = 0; w < NT / 32; w++) b += wsm[w * 4 + threadIdx.x];
         a.part[which][(long long)blockIdx.x * 4 + threadIdx.x] = b;
     }
     __syncthreads();
@@ -1044,9 +1044,11 @@ __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double 
     __syncthreads();
     gen += 1ull;
     if (!WORLD) {
-        // every block sums all partials itself: warp `wid` sums value `wid` over the blocks in the fixed order
-        const double t = warp_sum(lane_strided_sum(a.part[which], (int)gridDim.x, 4, wid, lane));
-        if (lane == 0) s_tot[wid] = t;
+        // every block sums all partials itself: warp `wid` (< 4) sums value `wid` over the blocks in the fixed order
+        if (wid < 4) {
+            const double t = warp_sum(lane_strided_sum(a.part[which], (int)gridDim.x, 4, wid, lane));
+            if (lane == 0) s_tot[wid] = t;
+        }
         __syncthreads();
     } else {
         // The last block to arrive sums the partials and stores this rank's four totals, as self-validating words
@@ -1061,8 +1063,10 @@ __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double 
         __shared__ unsigned s_word[MAX_RANKS][8];
         if (s_islast) {
             __threadfence();
-            const double tt = warp_sum(lane_strided_sum(a.part[which], (int)gridDim.x, 4, wid, lane));
-            if (lane == 0) s_tot[wid] = tt;
+            if (wid < 4) {
+                const double tt = warp_sum(lane_strided_sum(a.part[which], (int)gridDim.x, 4, wid, lane));
+                if (lane == 0) s_tot[wid] = tt;
+            }
             __syncthreads();
             if (talker) {
                 const unsigned long long bits = (unsigned long long)__double_as_longlong(s_tot[w >> 1]);
@@ -1102,12 +1106,18 @@ __device__ __forceinline__ void grid_allreduce4(const PersistentArgs& a, double 
 // 4 (128 registers, 0.9 KB of spills per thread) puts a third more warps on an SM and shortens the chunk a warp walks,
 // but measured (round 2, SRPS_PF_MINB=4) 3.22 against 2.18 ms per outer iteration at 1080p and 3.57 against 2.73 ms on
 // a 2 M-pixel strip: rejected, kept as a switch for the record.
-template <int SF, int COH, int MINB = SRPS_FUSED_MINB>
-__global__ void __launch_bounds__(SW_NT, MINB) cg_persistent_fused_kernel(const PersistentArgs a) {
-    static_assert(SW_NT / 32 == 4, "one warp per dot in grid_allreduce4");
+// NT: threads per CTA.  128 x 3 CTAs per SM is the geometry of the one-launch-per-pass kernels; 384 x 1 (SRPS_PF_NT=384) puts the
+// same twelve warps into ONE CTA per SM: a third of the arrivals at the grid barrier and a third of the partials every block
+// sums per pass.  Measured (round 2): slower -- 1080p 2.23 against 2.20 ms per outer iteration, a 512^2 scene 1.38 against
+// 1.02 ms (twelve warps wait at every __syncthreads of the barrier, and a small scene occupies a third of the SMs): the
+// barrier's cost is its chain of dependent L2 round trips (fence, arrival, poll, partial sums), not the number of arrivals.
+// A pause between two polls of the barrier words (SRPS_POLL_NS) changes nothing either.  Both kept as switches for the record.
+template <int SF, int COH, int MINB = SRPS_FUSED_MINB, int NT = SW_NT>
+__global__ void __launch_bounds__(NT, MINB) cg_persistent_fused_kernel(const PersistentArgs a) {
+    static_assert(NT / 32 >= 4, "one warp per dot in grid_allreduce4");
     static_assert(COH == 1 || COH == 2, "1: single GPU, 2: strip partition (planes are rewritten inside this launch: coherent loads)");
     constexpr bool WORLD = (COH == 2);
-    __shared__ double wsm[(SW_NT / 32) * 4];
+    __shared__ double wsm[(NT / 32) * 4];
     __shared__ double s_tot[4];
     CgScalars* sc = a.st.sc;
     if (!sc->active) return;                         // r.r <= tol^2 already after the residual kernel (uniform, also over the ranks)
@@ -1140,11 +1150,11 @@ __global__ void __launch_bounds__(SW_NT, MINB) cg_persistent_fused_kernel(const 
             v[0] = fused_update_only<1, WORLD>(st, alpha, tag_in);
         } else {
             double ex[3];
-            v[1] = (pass == 0) ? strip_pass<MODE_FUSED0, SF, 1, WORLD>(st, lc, 0.f, 0.f, ex, tag_in)
-                               : strip_pass<MODE_FUSED, SF, 1, WORLD>(st, lc, beta, alpha, ex, tag_in);
+            v[1] = (pass == 0) ? strip_pass<MODE_FUSED0, SF, 1, WORLD, NT>(st, lc, 0.f, 0.f, ex, tag_in)
+                               : strip_pass<MODE_FUSED, SF, 1, WORLD, NT>(st, lc, beta, alpha, ex, tag_in);
             v[0] = ex[0]; v[2] = ex[1]; v[3] = ex[2];
         }
-        grid_allreduce4<WORLD>(a, v, pass & 1, gen, wsm, s_tot, (unsigned long long)tag0 + (unsigned long long)pass + 1ull);
+        grid_allreduce4<WORLD, NT>(a, v, pass & 1, gen, wsm, s_tot, (unsigned long long)tag0 + (unsigned long long)pass + 1ull);
         const double S0 = v[0], S1 = v[1], S3 = v[3];
         if (!((float)S0 > tol2)) {                   // void pass, see cg_fused_kernel
             r1 = S0;
@@ -1172,8 +1182,8 @@ __global__ void __launch_bounds__(SW_NT, MINB) cg_persistent_fused_kernel(const 
     }
     if (alpha != 0.f) {                              // z += alpha p of the last valid pass (the last barrier ordered p)
         const float* p = a.pp[plane];
-        const long long stride = (long long)gridDim.x * SW_NT;
-        for (long long i = (long long)blockIdx.x * SW_NT + threadIdx.x; i < a.n4; i += stride) {
+        const long long stride = (long long)gridDim.x * NT;
+        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < a.n4; i += stride) {
             const float4 p4 = __ldcg(reinterpret_cast<const float4*>(p + 4 * i));
             float4 x4 = ld4(a.x + 4 * i);
             x4.x += alpha * p4.x; x4.y += alpha * p4.y; x4.z += alpha * p4.z; x4.w += alpha * p4.w;
