@@ -73,6 +73,7 @@ struct srps_ctx {
     int grid_stencil = 0, grid_update = 0, grid_stack = 0, grid_light_x = 0, light_groups = 0, grid_ep = 0, grid_al = 0, grid_gram = 0;
     int tiles_x = 0, tiles_y = 0;
     int use_strip = 0, strip_n = 0, strip_chunks = 0, strip_cl = 0, grid_strip = 0;
+    int init_chunks = 0, init_cl = 0, grid_init = 0;  // chunk geometry of the residual kernel in its warp-strip form (2 CTAs per SM)
     int use_persistent = 0, grid_persistent = 0;      // all CG passes in one cooperative launch
     int use_persistent_fused = 0;                     // ... in the fused form (one grid barrier per pass; opt-in)
     int pf_minb = 3;                                  // CTAs per SM the persistent fused kernel is compiled for (SRPS_PF_MINB)
@@ -199,6 +200,10 @@ static const void* fn_fused_tma(int sf, bool world) {
                                                                                    : (const void*)cg_fused_tma_kernel<4, true>);
     return sf == 1 ? (const void*)cg_fused_tma_kernel<1, false> : (sf == 2 ? (const void*)cg_fused_tma_kernel<2, false>
                                                                           : (const void*)cg_fused_tma_kernel<4, false>);
+}
+static const void* fn_strip_init(int sf) {
+    return sf == 1 ? (const void*)stencil_strip_init_kernel<1> : (sf == 2 ? (const void*)stencil_strip_init_kernel<2>
+                                                                          : (const void*)stencil_strip_init_kernel<4>);
 }
 static const void* fn_persistent(int sf) {
     return sf == 1 ? (const void*)cg_persistent_kernel<1> : (sf == 2 ? (const void*)cg_persistent_kernel<2> : (const void*)cg_persistent_kernel<4>);
@@ -432,6 +437,14 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         ctx->strip_chunks = (g.ny + cl - 1) / cl;
         const int nitems = ctx->strip_n * ctx->strip_chunks;
         ctx->grid_strip = std::min((nitems + SW_NT / 32 - 1) / (SW_NT / 32), ctx->sm_count * occ);
+        {   // the residual kernel (stencil_strip_init_kernel) runs at its own occupancy: one item per resident warp there too
+            const int occ_i = std::max(1, occupancy(fn_strip_init(sfk), SW_NT));
+            const int chunks_i = std::max(1, ctx->sm_count * occ_i * (SW_NT / 32) / ctx->strip_n);
+            ctx->init_cl = std::min(256, std::max(8, round_up((g.ny + chunks_i - 1) / chunks_i, SW_G)));
+            ctx->init_chunks = (g.ny + ctx->init_cl - 1) / ctx->init_cl;
+            const int items_i = ctx->strip_n * ctx->init_chunks;
+            ctx->grid_init = std::min((items_i + SW_NT / 32 - 1) / (SW_NT / 32), ctx->sm_count * occ_i);
+        }
         ctx->grid_persistent = ctx->grid_strip;            // <= sm_count * occ_p: all blocks co-resident
         if (ctx->use_persistent_fused && ctx->pf_nt != SW_NT) {
             const int wpb = ctx->pf_nt / 32;
@@ -453,7 +466,7 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, normals_energy_kernel<true>, EP_NT, 0));
     ctx->grid_ep = (int)std::min<long long>((ctx->n4 + EP_NT - 1) / EP_NT, (long long)ctx->sm_count * std::max(1, occ));
     ctx->grid_al = (int)std::min<long long>((ctx->n4 + AL_NT - 1) / AL_NT, (long long)ctx->sm_count * 4);
-    long long pl = std::max<long long>({(long long)ctx->grid_stencil, 8ll * ctx->grid_strip, (long long)ctx->grid_update, (long long)ctx->grid_ep,
+    long long pl = std::max<long long>({(long long)ctx->grid_stencil, 8ll * ctx->grid_strip, (long long)ctx->grid_init, (long long)ctx->grid_update, (long long)ctx->grid_ep,
                                         3ll * ctx->grid_al, 30ll * ctx->grid_gram,
                                         (long long)LIGHT_IB * 12 * ctx->grid_light_x * ctx->light_groups}) + 64;
     ctx->partials_len = pl;
@@ -951,7 +964,15 @@ static int depth_enqueue(srps_ctx* ctx, int slot) {
     if ((rc = halo_push(ctx, {ctx->z, ctx->w[0], ctx->w[1], ctx->w[2], ctx->gq[0]}))) return rc;    // strip partition: ghosts of the operands
     StencilArgs si = sa;
     si.y = ctx->r;
-    LAUNCH(ctx, stencil_kernel<MODE_INIT>, ctx->grid_stencil, CG_NT, si);
+    const char* ri = getenv("SRPS_RESIDUAL");
+    if (ctx->use_strip && !(ri && strcmp(ri, "tile") == 0)) {       // warp-strip form (sf <= 4); SRPS_RESIDUAL=tile: the round-1 kernel
+        si.strip_cl = ctx->init_cl; si.strip_chunks = ctx->init_chunks;
+        void* kargs[] = {(void*)&si};
+        CK(cudaLaunchKernel(fn_strip_init(ctx->g.sf), dim3(ctx->grid_init), dim3(SW_NT), kargs, 0, ctx->stream));
+        ctx->launches++;
+    } else {
+        LAUNCH(ctx, stencil_kernel<MODE_INIT>, ctx->grid_stencil, CG_NT, si);
+    }
     CK(cudaGetLastError());
     // (the ghost lines of r are pulled from the neighbours inside the operator kernel: no push here; the r.r all-reduce
     //  at the end of the residual kernel orders the neighbours' writes before the first pass)

@@ -636,6 +636,161 @@ __global__ void __launch_bounds__(SW_NT, SRPS_STRIP_MINB) stencil_strip_kernel(c
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The residual of the depth system in the warp-strip form (sf <= 4), once per outer iteration:
+//     r = Kt (z0s - K z) + G^T (g - M G z) ,  r1 = r.r          devicecalls.cu:743-745,758 ; :242-252
+// Same walk as strip_pass<MODE_APPLY> with z as the operand, plus the right-hand-side planes g0..2 of every line and the
+// LR depth of every block.  Replaces stencil_kernel<MODE_INIT> (the shared-memory tile kernel, 0.44 of the HBM peak) on
+// this path; 2 CTAs per SM (the three g planes of a 5-line window do not fit 168 registers), own chunk geometry.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ LineQ line_q_init(const LightConsts& lc, float fx, float fy, float xx, float yy0, unsigned t4,
+                                             const float4& pc, const float4& up, const float4& dn, float left, float right,
+                                             const float4& w0, const float4& w1, const float4& w2, const float4& g0, const float4& g1,
+                                             const float4& g2) {
+    LineQ o;
+    const float pcv[6] = {left, pc.x, pc.y, pc.z, pc.w, right};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const unsigned t = (t4 >> (8 * k)) & 0xffu;
+        const float c = pcv[k + 1];
+        const float dxp = (t & T_XF) ? f4get(dn, k) - c : ((t & T_XB) ? c - f4get(up, k) : 0.f);
+        const float dyp = (t & T_YF) ? pcv[k + 2] - c : ((t & T_YB) ? c - pcv[k] : 0.f);
+        const Qm m = make_qm(lc, f4get(w0, k), f4get(w1, k), f4get(w2, k));
+        float q0, q1, q2;
+        apply_m(m, fx, fy, xx, yy0 + (float)k, dxp, dyp, c, q0, q1, q2);
+        q0 = f4get(g0, k) - q0; q1 = f4get(g1, k) - q1; q2 = f4get(g2, k) - q2;          // g - M G z
+        const float a0 = (t & T_XF) ? q0 : 0.f, b0 = (t & T_XB) ? q0 : 0.f;
+        const float a1 = (t & T_YF) ? q1 : 0.f, b1 = (t & T_YB) ? q1 : 0.f;
+        f4set(o.q0f, k, a0); f4set(o.q0b, k, b0); f4set(o.q1f, k, a1); f4set(o.q1b, k, b1);
+        f4set(o.own, k, q2 - a0 + b0 - a1 + b1);
+    }
+    return o;
+}
+
+template <int SF>
+__global__ void __launch_bounds__(SW_NT, 2) stencil_strip_init_kernel(const StencilArgs a) {
+    static_assert(SF == 1 || SF == 2 || SF == 4, "sf must divide the group height");
+    __shared__ double red[SW_NT / 32];
+    const LightConsts& lc = c_lc[a.lc_slot];
+    const Grid& g = a.g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pitch = g.pitch, ny = g.ny;
+    const float inv2 = 1.f / (float)(SF * SF);
+    const unsigned FULL = 0xffffffffu;
+    const int nitems = a.strip_n * a.strip_chunks;
+    double dot = 0.0;
+    for (int item = blockIdx.x * (SW_NT / 32) + warp; item < nitems; item += gridDim.x * (SW_NT / 32)) {
+        const int strip = item % a.strip_n, chunk = item / a.strip_n;
+        const int x = 4 * (strip * SW_COLS - 1 + lane);
+        const bool colok = x < pitch;
+        const bool writer = (lane >= 1) && (lane <= SW_COLS) && colok;
+        const int jA = chunk * a.strip_cl;
+        const int jB = min(jA + a.strip_cl, ny);
+        const float yy0 = (float)(g.ib0 + x) - g.cy;
+        auto off_of = [&](int j) -> long long { return (colok && j <= ny) ? (long long)j * pitch + x : 0; };   // clamped, see strip_pass
+
+        float4 pl[SW_G + 1], wl0[SW_G + 1], wl1[SW_G + 1], wl2[SW_G + 1], gl0[SW_G + 1], gl1[SW_G + 1], gl2[SW_G + 1];
+        unsigned tl[SW_G + 1];
+        float4 pprev, q0f_prev;
+        {   // prologue: the forward x-rows of line jA-1 reach line jA
+            const long long op = off_of(jA - 1), oa = off_of(jA);
+            pprev = ldg4(a.vin + op);
+            const unsigned tp = __ldg(reinterpret_cast<const unsigned*>(a.types + op));
+            const float4 w0 = ldg4(a.w0 + op), w1 = ldg4(a.w1 + op), w2 = ldg4(a.w2 + op), gp0 = ldg4(a.g0 + op);
+            pl[0] = ldg4(a.vin + oa);
+            tl[0] = __ldg(reinterpret_cast<const unsigned*>(a.types + oa));
+            wl0[0] = ldg4(a.w0 + oa); wl1[0] = ldg4(a.w1 + oa); wl2[0] = ldg4(a.w2 + oa);
+            gl0[0] = ldg4(a.g0 + oa); gl1[0] = ldg4(a.g1 + oa); gl2[0] = ldg4(a.g2 + oa);
+            const float left = __shfl_up_sync(FULL, pprev.w, 1), right = __shfl_down_sync(FULL, pprev.x, 1);
+            const float xx = (float)(g.jb0 + jA - 1) - g.cx;
+            const LineQ q = line_q_init(lc, g.fx, g.fy, xx, yy0, tp & 0xfbfbfbfbu, pprev, f4zero(), pl[0], left, right, w0, w1, w2, gp0,
+                                        f4zero(), f4zero());
+            q0f_prev = q.q0f;
+        }
+        for (int j0 = jA; j0 < jB; j0 += SW_G) {
+#pragma unroll
+            for (int l = 1; l <= SW_G; l++) {
+                const long long o = off_of(j0 + l);
+                pl[l] = ldg4(a.vin + o);
+                tl[l] = __ldg(reinterpret_cast<const unsigned*>(a.types + o));
+                wl0[l] = ldg4(a.w0 + o); wl1[l] = ldg4(a.w1 + o); wl2[l] = ldg4(a.w2 + o);
+                gl0[l] = ldg4(a.g0 + o); gl1[l] = ldg4(a.g1 + o); gl2[l] = ldg4(a.g2 + o);
+            }
+            // LR depth of the blocks this lane's 4 pixels x 4 lines belong to (clamped like the planes: never used outside T_LR pixels)
+            float z0v[SW_G][4];
+#pragma unroll
+            for (int l = 0; l < SW_G; l++) {
+                const int jl = min(j0 + l, ny - 1) / SF;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int xc = min(max(x + k, 0), g.nx - 1) / SF;
+                    z0v[l][k] = ((SF == 4 && (l > 0 || k > 0)) || (SF == 2 && ((l & 1) || (k & 1)))) ? 0.f : __ldg(a.z0lr + (long long)jl * g.lpitch + xc);
+                }
+            }
+            float bs4 = 0.f, bs2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+            if (SF == 4) {
+#pragma unroll
+                for (int l = 0; l < SW_G; l++) bs4 += (pl[l].x + pl[l].y) + (pl[l].z + pl[l].w);
+            } else if (SF == 2) {
+#pragma unroll
+                for (int l = 0; l < SW_G; l++) { bs2[l / 2][0] += pl[l].x + pl[l].y; bs2[l / 2][1] += pl[l].z + pl[l].w; }
+            }
+#pragma unroll
+            for (int l = 0; l < SW_G; l++) {
+                const int j = j0 + l;
+                const float4 pc = pl[l];
+                const float4 up = (l == 0) ? pprev : pl[l > 0 ? l - 1 : 0];
+                const float left = __shfl_up_sync(FULL, pc.w, 1), right = __shfl_down_sync(FULL, pc.x, 1);
+                const float xx = (float)(g.jb0 + j) - g.cx;
+                const LineQ q = line_q_init(lc, g.fx, g.fy, xx, yy0, tl[l], pc, up, pl[l + 1], left, right, wl0[l], wl1[l], wl2[l], gl0[l], gl1[l], gl2[l]);
+                float4 q0b_dn = f4zero();
+                const unsigned tn = tl[l + 1];
+                if (__any_sync(FULL, (tn & 0x04040404u) != 0u)) {
+                    const float4 pn = pl[l + 1];
+                    const float ln = __shfl_up_sync(FULL, pn.w, 1), rn = __shfl_down_sync(FULL, pn.x, 1);
+                    const LineQ qn = line_q_init(lc, g.fx, g.fy, xx + 1.f, yy0, tn & 0xfdfdfdfdu, pn, pc, f4zero(), ln, rn, wl0[l + 1], wl1[l + 1],
+                                                 wl2[l + 1], gl0[l + 1], f4zero(), f4zero());
+                    q0b_dn = qn.q0b;
+                }
+                const float q1f_left = __shfl_up_sync(FULL, q.q1f.w, 1), q1b_right = __shfl_down_sync(FULL, q.q1b.x, 1);
+                const float q1fv[5] = {q1f_left, q.q1f.x, q.q1f.y, q.q1f.z, q.q1f.w};
+                const float q1bv[5] = {q.q1b.x, q.q1b.y, q.q1b.z, q.q1b.w, q1b_right};
+                float4 out;
+                float dl = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const unsigned t = (tl[l] >> (8 * k)) & 0xffu;
+                    float yv = f4get(q.own, k) + f4get(q0f_prev, k) - f4get(q0b_dn, k) + q1fv[k] - q1bv[k + 1];
+                    if (t & T_LR) {
+                        const float bs = (SF == 4) ? bs4 : ((SF == 2) ? bs2[l / 2][k / 2] : f4get(pc, k));
+                        const float z0 = (SF == 4) ? z0v[0][0] : ((SF == 2) ? z0v[l & ~1][k & ~1] : z0v[l][k]);
+                        yv += (z0 - bs * inv2) * inv2;
+                    }
+                    if (!(t & T_MASK)) yv = 0.f;
+                    f4set(out, k, yv);
+                    dl += yv * yv;
+                }
+                if (writer && j < jB) {
+                    st4(a.y + (long long)j * pitch + x, out);
+                    dot += (double)dl;
+                }
+                q0f_prev = q.q0f;
+            }
+            pprev = pl[SW_G - 1];
+            pl[0] = pl[SW_G]; tl[0] = tl[SW_G]; wl0[0] = wl0[SW_G]; wl1[0] = wl1[SW_G]; wl2[0] = wl2[SW_G];
+            gl0[0] = gl0[SW_G]; gl1[0] = gl1[SW_G]; gl2[0] = gl2[SW_G];
+        }
+    }
+    double total;
+    if (grid_reduce_last_world<SW_NT>(dot, a.partials, a.ticket, red, total, a.comm)) {
+        if (threadIdx.x == 0) {                  // r1 = b.b ; k = 0          devicecalls.cu:242-252
+            CgScalars* s = a.sc;
+            s->r1 = total; s->r0 = 0.0; s->k = 0; s->beta = 0.f; s->alpha = 0.f; s->defer = 0; s->n_defer = 0;
+            s->active = ((float)total > s->tol2) && (0 <= s->max_iter);
+        }
+    }
+}
+
 // x += alpha p ; r -= alpha y ; r1 = r.r ; beta = r1/r0 ; k++        devicecalls.cu:270-274,262
 struct UpdateArgs {
     float* x; float* r; const float* p; const float* y;

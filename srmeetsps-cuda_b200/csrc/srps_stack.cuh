@@ -234,25 +234,83 @@ __global__ void __launch_bounds__(ST_NT, SRPS_LIGHT_MINB) lighting_reduce_kernel
 #pragma unroll
     for (int i = 0; i < LIGHT_IB * 12; i++) acc[i] = 0.f;
     const long long stride = (long long)gridDim.x * ST_NT;
-    for (long long i = (long long)blockIdx.x * ST_NT + threadIdx.x; i < a.n4; i += stride) {
-        const float4 n0 = ld4(a.N[0] + 4 * i), n1 = ld4(a.N[1] + 4 * i), n2 = ld4(a.N[2] + 4 * i);
+    // one float4 of pixels: acc += over c, images -- the accumulation order every variant below keeps
+    auto accumulate = [&](const float4& n0, const float4& n1, const float4& n2, const float4 (&r)[3], const float4 (&v)[3][LIGHT_IB]) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const float4 r = ld4(a.rho[c] + 4 * i);
-            float4 v[LIGHT_IB];
-#pragma unroll
-            for (int ii = 0; ii < LIGHT_IB; ii++)
-                v[ii] = (ii < nimg) ? ld_stack4<T>(stack + ((long long)(i0 + ii) * 3 + c) * a.plane, i) : f4zero();
-            const float4 a0 = make_float4(r.x * n0.x, r.y * n0.y, r.z * n0.z, r.w * n0.w);
-            const float4 a1 = make_float4(r.x * n1.x, r.y * n1.y, r.z * n1.z, r.w * n1.w);
-            const float4 a2 = make_float4(r.x * n2.x, r.y * n2.y, r.z * n2.z, r.w * n2.w);
+            const float4 a0 = make_float4(r[c].x * n0.x, r[c].y * n0.y, r[c].z * n0.z, r[c].w * n0.w);
+            const float4 a1 = make_float4(r[c].x * n1.x, r[c].y * n1.y, r[c].z * n1.z, r[c].w * n1.w);
+            const float4 a2 = make_float4(r[c].x * n2.x, r[c].y * n2.y, r[c].z * n2.z, r[c].w * n2.w);
 #pragma unroll
             for (int ii = 0; ii < LIGHT_IB; ii++) {
                 float* o = acc + (ii * 3 + c) * 4;
-                o[0] += v[ii].x * a0.x + v[ii].y * a0.y + v[ii].z * a0.z + v[ii].w * a0.w;
-                o[1] += v[ii].x * a1.x + v[ii].y * a1.y + v[ii].z * a1.z + v[ii].w * a1.w;
-                o[2] += v[ii].x * a2.x + v[ii].y * a2.y + v[ii].z * a2.z + v[ii].w * a2.w;
-                o[3] += v[ii].x * r.x + v[ii].y * r.y + v[ii].z * r.z + v[ii].w * r.w;
+                o[0] += v[c][ii].x * a0.x + v[c][ii].y * a0.y + v[c][ii].z * a0.z + v[c][ii].w * a0.w;
+                o[1] += v[c][ii].x * a1.x + v[c][ii].y * a1.y + v[c][ii].z * a1.z + v[c][ii].w * a1.w;
+                o[2] += v[c][ii].x * a2.x + v[c][ii].y * a2.y + v[c][ii].z * a2.z + v[c][ii].w * a2.w;
+                o[3] += v[c][ii].x * r[c].x + v[c][ii].y * r[c].y + v[c][ii].z * r[c].z + v[c][ii].w * r[c].w;
+            }
+        }
+    };
+    if (sizeof(T) == 4) {
+        for (long long i = (long long)blockIdx.x * ST_NT + threadIdx.x; i < a.n4; i += stride) {
+            const float4 n0 = ld4(a.N[0] + 4 * i), n1 = ld4(a.N[1] + 4 * i), n2 = ld4(a.N[2] + 4 * i);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float4 r = ld4(a.rho[c] + 4 * i);
+                float4 v[LIGHT_IB];
+#pragma unroll
+                for (int ii = 0; ii < LIGHT_IB; ii++)
+                    v[ii] = (ii < nimg) ? ld_stack4<T>(stack + ((long long)(i0 + ii) * 3 + c) * a.plane, i) : f4zero();
+                const float4 a0 = make_float4(r.x * n0.x, r.y * n0.y, r.z * n0.z, r.w * n0.w);
+                const float4 a1 = make_float4(r.x * n1.x, r.y * n1.y, r.z * n1.z, r.w * n1.w);
+                const float4 a2 = make_float4(r.x * n2.x, r.y * n2.y, r.z * n2.z, r.w * n2.w);
+#pragma unroll
+                for (int ii = 0; ii < LIGHT_IB; ii++) {
+                    float* o = acc + (ii * 3 + c) * 4;
+                    o[0] += v[ii].x * a0.x + v[ii].y * a0.y + v[ii].z * a0.z + v[ii].w * a0.w;
+                    o[1] += v[ii].x * a1.x + v[ii].y * a1.y + v[ii].z * a1.z + v[ii].w * a1.w;
+                    o[2] += v[ii].x * a2.x + v[ii].y * a2.y + v[ii].z * a2.z + v[ii].w * a2.w;
+                    o[3] += v[ii].x * r.x + v[ii].y * r.y + v[ii].z * r.z + v[ii].w * r.w;
+                }
+            }
+        }
+    } else {
+        // 8-bit samples: a float4 of pixels is ONE 4-byte load per plane, so a thread keeps a quarter of the bytes in flight;
+        // two pixel groups (i, i + stride) are loaded together -- all channels, all images -- before either is accumulated, in
+        // the same order as above (the sums stay bit-identical to the float stack's).
+        for (long long i = (long long)blockIdx.x * ST_NT + threadIdx.x; i < a.n4; i += 2 * stride) {
+            const long long ib = i + stride;
+            const bool hb = ib < a.n4;
+            const long long jb = hb ? ib : i;
+            unsigned ua[3][LIGHT_IB], ub[3][LIGHT_IB];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int ii = 0; ii < LIGHT_IB; ii++) {
+                    const unsigned char* pl = reinterpret_cast<const unsigned char*>(stack) + ((long long)(i0 + min(ii, nimg - 1)) * 3 + c) * a.plane;
+                    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(ua[c][ii]) : "l"(pl + 4 * i));
+                    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(ub[c][ii]) : "l"(pl + 4 * jb));
+                }
+            const float4 na0 = ld4(a.N[0] + 4 * i), na1 = ld4(a.N[1] + 4 * i), na2 = ld4(a.N[2] + 4 * i);
+            const float4 ra[3] = {ld4(a.rho[0] + 4 * i), ld4(a.rho[1] + 4 * i), ld4(a.rho[2] + 4 * i)};
+            const float4 nb0 = ld4(a.N[0] + 4 * jb), nb1 = ld4(a.N[1] + 4 * jb), nb2 = ld4(a.N[2] + 4 * jb);
+            const float4 rb[3] = {ld4(a.rho[0] + 4 * jb), ld4(a.rho[1] + 4 * jb), ld4(a.rho[2] + 4 * jb)};
+            float4 v[3][LIGHT_IB];
+            auto unpack = [&](const unsigned (&u)[3][LIGHT_IB]) {
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int ii = 0; ii < LIGHT_IB; ii++) {
+                        const unsigned w = u[c][ii];
+                        v[c][ii] = (ii < nimg) ? make_float4(u8_to_unit(w & 0xffu), u8_to_unit((w >> 8) & 0xffu), u8_to_unit((w >> 16) & 0xffu), u8_to_unit(w >> 24))
+                                               : f4zero();
+                    }
+            };
+            unpack(ua);
+            accumulate(na0, na1, na2, ra, v);
+            if (hb) {
+                unpack(ub);
+                accumulate(nb0, nb1, nb2, rb, v);
             }
         }
     }
@@ -369,7 +427,9 @@ __global__ void __launch_bounds__(ST_NT, SRPS_PROJ_MINB) stack_project_kernel(co
 #pragma unroll
             for (int k = 0; k < 4; k++) U[c][k] = f4zero();
         }
-#pragma unroll PROJ_UNROLL
+        // 8-bit samples: twice the images in flight (a plane's float4 of pixels is a 4-byte load)
+        constexpr int UN = sizeof(T) == 1 ? 2 * PROJ_UNROLL : PROJ_UNROLL;
+#pragma unroll UN
         for (int j = 0; j < a.n_images; j++) {
             float4 v[3];
 #pragma unroll
