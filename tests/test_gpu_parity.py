@@ -127,6 +127,33 @@ def test_depth_operator_matches_assembled_matrix(cfg, stencil, monkeypatch):
     ctx.close()
 
 
+@pytest.mark.parametrize("kernel", ["strip", "tile"])
+@pytest.mark.parametrize("cfg", SCENES, ids=lambda c: f"{c['h']}x{c['w']}sf{c['sf']}{c['mask_kind']}")
+def test_residual_kernel_matches_assembled_system(cfg, kernel, monkeypatch):
+    """r = Kt (z0s - K z) + G^T (g - M G z) from both residual kernels (warp-strip form for sf <= 4, shared-memory tile)
+    against rhs - A z of the oracle's assembled fp64 system.  A huge CG tolerance makes srps_depth stop right after the
+    residual kernel, so the residual plane holds its output."""
+    monkeypatch.setenv("SRPS_RESIDUAL", kernel)
+    sc = scene(cfg)
+    ctx = make_ctx(sc, cg_tol=1e18)
+    rng = np.random.default_rng(0)
+    s = (0.5 * rng.standard_normal((sc["n"], 3, 4))).astype(np.float32)
+    ctx.set_state("s", s)
+    ctx.albedo()
+    rho, dz = ctx.download("rho"), ctx.download("dz")
+    z_before = ctx.download("z")
+    e, k = ctx.depth()
+    assert k == 0 and np.array_equal(ctx.download("z"), z_before)
+    r = ctx.download("r")
+    st = oracle_state(sc, np.float64)
+    _, _, _, mf = o.depth_update_matfree(s.astype(np.float64), rho.astype(np.float64), st["I"], st["xx"], st["yy"],
+                                         dz.astype(np.float64), sc["ops"], st["z0s"], st["z"], st["fx"], st["fy"], np.float64)
+    ref = mf["rhs"] - mf["Aop"](st["z"])
+    scale = max(np.abs(mf["rhs"]).max(), np.abs(mf["Aop"](st["z"])).max())
+    assert np.abs(r - ref).max() <= 2e-5 * scale, (np.abs(r - ref).max(), scale)
+    ctx.close()
+
+
 @pytest.mark.parametrize("cfg", SCENES[2:6], ids=lambda c: f"{c['h']}x{c['w']}sf{c['sf']}{c['mask_kind']}")
 def test_single_phases_match_oracle(cfg):
     sc = scene(cfg)
@@ -174,7 +201,7 @@ def test_outer_iterations_match_oracle(cfg, albedo_mode):
     for it in range(3):
         e_ref, k_ref, _ = pt.outer_iteration(stp)
         e_gpu, k_gpu = ctx.outer_iteration()
-        assert abs(k_gpu - k_ref) <= 1
+        assert abs(k_gpu - k_ref) <= (1 if k_ref == 101 else 2), (k_gpu, k_ref)      # an early stop may shift by two passes (see below)
         z, rho = ctx.download("z"), ctx.download("rho")
         z64, rho64 = truth[it]
         assert within(rel_rmse(z, stp["z"]), t["z"], rel_rmse(z, z64), rel_rmse(stp["z"], z64)), \
