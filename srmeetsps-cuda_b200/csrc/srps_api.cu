@@ -72,8 +72,8 @@ struct srps_ctx {
     // launch geometry
     int grid_stencil = 0, grid_update = 0, grid_stack = 0, grid_light_x = 0, light_groups = 0, grid_ep = 0, grid_al = 0, grid_gram = 0;
     int tiles_x = 0, tiles_y = 0;
-    int use_strip = 0, strip_n = 0, strip_chunks = 0, strip_cl = 0, grid_strip = 0;
-    int init_chunks = 0, init_cl = 0, grid_init = 0;  // chunk geometry of the residual kernel in its warp-strip form (2 CTAs per SM)
+    int use_strip = 0, strip_n = 0, strip_chunks = 0, strip_groups = 0, grid_strip = 0;
+    int init_chunks = 0, grid_init = 0;  // chunk geometry of the residual kernel in its warp-strip form (2 CTAs per SM)
     int use_persistent = 0, grid_persistent = 0;      // all CG passes in one cooperative launch
     int use_persistent_fused = 0;                     // ... in the fused form (one grid barrier per pass; opt-in)
     int pf_minb = 3;                                  // CTAs per SM the persistent fused kernel is compiled for (SRPS_PF_MINB)
@@ -429,19 +429,20 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         if (ctx->use_persistent) occ = ctx->use_persistent_fused ? occ_p : std::min(occ, occ_p);   // the solve is one launch of that kernel
         if (ctx->use_tma) occ = std::min(occ, occ_tma);    // the ring kernel is shared-memory bound: 2 CTAs per SM
         const int warps = ctx->sm_count * occ * (SW_NT / 32);
-        // one (strip, chunk) item per resident warp: as many chunks per strip as the warps allow, then the chunk length
-        const int chunks_max = std::max(1, warps / ctx->strip_n);
-        int cl = (g.ny + chunks_max - 1) / chunks_max;
-        cl = std::min(256, std::max(8, round_up(cl, SW_G)));
-        ctx->strip_cl = cl;
-        ctx->strip_chunks = (g.ny + cl - 1) / cl;
+        // one (strip, chunk) item per resident warp: as many chunks per strip as the warps allow, of balanced length
+        // (chunk_lines): at least 2 groups each (one prologue line per chunk), at most 64 (longer grids take several waves)
+        ctx->strip_groups = (g.ny + SW_G - 1) / SW_G;
+        auto chunks_for = [&](int warps_resident) {
+            int c = std::max(1, warps_resident / ctx->strip_n);
+            c = std::min(c, std::max(1, ctx->strip_groups / 2));
+            return std::max(c, (ctx->strip_groups + 63) / 64);
+        };
+        ctx->strip_chunks = chunks_for(warps);
         const int nitems = ctx->strip_n * ctx->strip_chunks;
         ctx->grid_strip = std::min((nitems + SW_NT / 32 - 1) / (SW_NT / 32), ctx->sm_count * occ);
         {   // the residual kernel (stencil_strip_init_kernel) runs at its own occupancy: one item per resident warp there too
             const int occ_i = std::max(1, occupancy(fn_strip_init(sfk), SW_NT));
-            const int chunks_i = std::max(1, ctx->sm_count * occ_i * (SW_NT / 32) / ctx->strip_n);
-            ctx->init_cl = std::min(256, std::max(8, round_up((g.ny + chunks_i - 1) / chunks_i, SW_G)));
-            ctx->init_chunks = (g.ny + ctx->init_cl - 1) / ctx->init_cl;
+            ctx->init_chunks = chunks_for(ctx->sm_count * occ_i * (SW_NT / 32));
             const int items_i = ctx->strip_n * ctx->init_chunks;
             ctx->grid_init = std::min((items_i + SW_NT / 32 - 1) / (SW_NT / 32), ctx->sm_count * occ_i);
         }
@@ -825,7 +826,7 @@ static void fill_stencil_args(srps_ctx* ctx, StencilArgs& sa) {
     sa.vin = ctx->z; sa.r = ctx->r; sa.p_in = ctx->p; sa.p_out = ctx->p2; sa.y = ctx->y; sa.g0 = ctx->gq[0]; sa.g1 = ctx->gq[1]; sa.g2 = ctx->gq[2];
     sa.z0lr = ctx->z0lr; sa.sc = ctx->sc; sa.partials = ctx->partials; sa.ticket = ctx->tickets + 4;
     sa.tiles_x = ctx->tiles_x; sa.tiles_y = ctx->tiles_y;
-    sa.strip_n = ctx->strip_n; sa.strip_chunks = ctx->strip_chunks; sa.strip_cl = ctx->strip_cl;
+    sa.strip_n = ctx->strip_n; sa.strip_chunks = ctx->strip_chunks; sa.strip_groups = ctx->strip_groups;
     sa.comm = ctx->comm;
     peer_boundary_lines(ctx, ctx->r, sa.r_prev_line, sa.r_next_line);
     sa.y_in = nullptr; sa.r_out = nullptr; sa.x = nullptr; sa.y_prev_line = nullptr; sa.y_next_line = nullptr; sa.plane = 0;
@@ -966,7 +967,7 @@ static int depth_enqueue(srps_ctx* ctx, int slot) {
     si.y = ctx->r;
     const char* ri = getenv("SRPS_RESIDUAL");
     if (ctx->use_strip && !(ri && strcmp(ri, "tile") == 0)) {       // warp-strip form (sf <= 4); SRPS_RESIDUAL=tile: the round-1 kernel
-        si.strip_cl = ctx->init_cl; si.strip_chunks = ctx->init_chunks;
+        si.strip_chunks = ctx->init_chunks;
         void* kargs[] = {(void*)&si};
         CK(cudaLaunchKernel(fn_strip_init(ctx->g.sf), dim3(ctx->grid_init), dim3(SW_NT), kargs, 0, ctx->stream));
         ctx->launches++;

@@ -47,7 +47,7 @@ struct StencilArgs {
     double* partials;
     unsigned* ticket;
     int tiles_x, tiles_y;
-    int strip_n, strip_chunks, strip_cl;   // warp-strip kernel: strips per line, chunks per strip, lines per chunk
+    int strip_n, strip_chunks, strip_groups;   // warp-strip kernel: strips per line, chunks per strip, 4-line groups per strip (chunk_lines)
     PeerComm comm;                         // world == 1: single GPU
     // strip partition: the residual on the two ghost lines is PULLED from the neighbours' boundary lines (mapped peer
     // pointers; nullptr at the ends of the image).  The r.r all-reduce that ends every update kernel guarantees that the
@@ -345,6 +345,14 @@ constexpr int SW_G = 4;          // lines per group (multiple of sf)
 // cost more than the latency they hide.
 struct LineQ { float4 q0f, q0b, q1f, q1b, own; };
 
+// Chunk c of the C = strip_chunks chunks of a strip covers the 4-line groups [c G / C, (c + 1) G / C) of the G = strip_groups
+// groups of the grid: lengths differ by at most one group, so every resident warp gets an item and none a much longer
+// one (a uniform chunk length rounded up to a group left 15 % of the warps idle at 1024 lines per GPU).
+__device__ __forceinline__ void chunk_lines(const StencilArgs& a, int chunk, int ny, int& jA, int& jB) {
+    jA = SW_G * (int)(((long long)chunk * a.strip_groups) / a.strip_chunks);
+    jB = min(ny, SW_G * (int)(((long long)(chunk + 1) * a.strip_groups) / a.strip_chunks));
+}
+
 __device__ __forceinline__ unsigned ld_types(const unsigned char* t, long long off) {
     return *reinterpret_cast<const unsigned*>(t + off);
 }
@@ -403,8 +411,8 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
         const int x = 4 * (strip * SW_COLS - 1 + lane);            // x = -4 on lane 0 of strip 0: the zero pad of the previous line
         const bool colok = x < pitch;
         const bool writer = (lane >= 1) && (lane <= SW_COLS) && colok;
-        const int jA = chunk * a.strip_cl;
-        const int jB = min(jA + a.strip_cl, ny);
+        int jA, jB;
+        chunk_lines(a, chunk, ny, jA, jB);
         const float yy0 = (float)(g.ib0 + x) - g.cy;
 
         // Loads are UNCONDITIONAL with a clamped address (the plane origin is always valid): no branch regions, so the
@@ -684,8 +692,8 @@ __global__ void __launch_bounds__(SW_NT, 2) stencil_strip_init_kernel(const Sten
         const int x = 4 * (strip * SW_COLS - 1 + lane);
         const bool colok = x < pitch;
         const bool writer = (lane >= 1) && (lane <= SW_COLS) && colok;
-        const int jA = chunk * a.strip_cl;
-        const int jB = min(jA + a.strip_cl, ny);
+        int jA, jB;
+        chunk_lines(a, chunk, ny, jA, jB);
         const float yy0 = (float)(g.ib0 + x) - g.cy;
         auto off_of = [&](int j) -> long long { return (colok && j <= ny) ? (long long)j * pitch + x : 0; };   // clamped, see strip_pass
 

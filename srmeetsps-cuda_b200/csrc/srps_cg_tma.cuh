@@ -67,8 +67,8 @@ __device__ __forceinline__ double strip_pass_tma(const StencilArgs& a, const Lig
         const int x = x0w + 4 * lane;
         const bool colok = x < pitch;
         const bool writer = (lane >= 1) && (lane <= SW_COLS) && colok;
-        const int jA = chunk * a.strip_cl;
-        const int jB = min(jA + a.strip_cl, ny);
+        int jA, jB;
+        chunk_lines(a, chunk, ny, jA, jB);
         const int ngroups = (jB - jA + SW_G - 1) / SW_G;      // ny is a multiple of sf only: the last group of the grid may be partial
         const float yy0 = (float)(g.ib0 + x) - g.cy;
 

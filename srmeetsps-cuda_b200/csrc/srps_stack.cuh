@@ -30,18 +30,27 @@ constexpr int MAX_IMAGES = 64; // n_images limit (shared-memory copy of s)
 // r = fl(1/255) -- which is the correctly rounded quotient for every v in 0..255 (checked exhaustively in exact
 // arithmetic, and by test_u8_upload_equals_float_upload on the device): 3 FP instructions instead of an IEEE division.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float u8_to_unit(unsigned v) {
-    const float f = (float)v;
+__device__ __forceinline__ float u8_unit_of(float f) {      // f = the sample as an exact float
     const float r = 1.f / 255.f;                    // folded at compile time
     const float q = f * r;
     return fmaf(fmaf(-255.f, q, f), r, q);
+}
+__device__ __forceinline__ float u8_to_unit(unsigned v) { return u8_unit_of((float)v); }
+// the four samples of a 32-bit word: byte k is placed under the exponent of 2^23 by one PRMT and the bias subtracted
+// (exact: no integer-to-float conversion instruction, which issues at a quarter of the FP rate)
+__device__ __forceinline__ float4 u8x4_to_unit(unsigned u) {
+    const float f0 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7540)) - 8388608.f;
+    const float f1 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7541)) - 8388608.f;
+    const float f2 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7542)) - 8388608.f;
+    const float f3 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7543)) - 8388608.f;
+    return make_float4(u8_unit_of(f0), u8_unit_of(f1), u8_unit_of(f2), u8_unit_of(f3));
 }
 template <typename T> __device__ __forceinline__ float4 ld_stack4(const T* plane, long long i4);
 template <> __device__ __forceinline__ float4 ld_stack4<float>(const float* plane, long long i4) { return ld4_stream(plane + 4 * i4); }
 template <> __device__ __forceinline__ float4 ld_stack4<unsigned char>(const unsigned char* plane, long long i4) {
     unsigned u;
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(u) : "l"(plane + 4 * i4));
-    return make_float4(u8_to_unit(u & 0xffu), u8_to_unit((u >> 8) & 0xffu), u8_to_unit((u >> 16) & 0xffu), u8_to_unit(u >> 24));
+    return u8x4_to_unit(u);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -302,8 +311,7 @@ __global__ void __launch_bounds__(ST_NT, SRPS_LIGHT_MINB) lighting_reduce_kernel
 #pragma unroll
                     for (int ii = 0; ii < LIGHT_IB; ii++) {
                         const unsigned w = u[c][ii];
-                        v[c][ii] = (ii < nimg) ? make_float4(u8_to_unit(w & 0xffu), u8_to_unit((w >> 8) & 0xffu), u8_to_unit((w >> 16) & 0xffu), u8_to_unit(w >> 24))
-                                               : f4zero();
+                        v[c][ii] = (ii < nimg) ? u8x4_to_unit(w) : f4zero();
                     }
             };
             unpack(ua);
