@@ -37,7 +37,9 @@ WORKLOADS = {
     "1080p": (1080, 1920, 4, 20, 1000),      # config 3
     "1k": (1024, 1024, 4, 32, 2000),         # the largest square both arms can run: the same-size pair of the reference ratio
     "small": (512, 512, 4, 8, 7),            # CI-sized
-    "n8sim": (4096, 1024, 4, 32, 2000),      # at 2 GPUs: the per-GPU strip of config 4 at 8 GPUs (512 lines x 4096 pixels)
+    "n8sim": (4096, 1024, 4, 32, 2000),      # at 2 GPUs: the per-GPU strip of config 4 at 8 GPUs (512 lines x 4096 pixels);
+                                             # at 1 GPU: the strip of config 4 at 4 GPUs without any exchange
+    "slab8": (4096, 512, 4, 32, 2000),       # at 1 GPU: the strip of config 4 at 8 GPUs without any exchange
 }
 PARITY_SCENE = (1024, 1024, 4, 8, 77, 3)     # strip_parity: h, w, sf, n, seed, outer iterations
 METRIC = "ms per outer iteration (4096x4096 HR, sf=4, 32 images)"

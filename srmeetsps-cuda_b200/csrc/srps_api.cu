@@ -73,7 +73,8 @@ struct srps_ctx {
     int grid_stencil = 0, grid_update = 0, grid_stack = 0, grid_light_x = 0, light_groups = 0, grid_ep = 0, grid_al = 0, grid_gram = 0;
     int tiles_x = 0, tiles_y = 0;
     int use_strip = 0, strip_n = 0, strip_chunks = 0, strip_groups = 0, grid_strip = 0;
-    int init_chunks = 0, grid_init = 0;  // chunk geometry of the residual kernel in its warp-strip form (2 CTAs per SM)
+    int init_chunks = 0, grid_init = 0;
+    size_t l2_window_bytes = 0; float l2_hit_ratio = 0.f;   // persisting-L2 window over the weight planes during the CG (0: off)  // chunk geometry of the residual kernel in its warp-strip form (2 CTAs per SM)
     int use_persistent = 0, grid_persistent = 0;      // all CG passes in one cooperative launch
     int use_persistent_fused = 0;                     // ... in the fused form (one grid barrier per pass; opt-in)
     int pf_minb = 3;                                  // CTAs per SM the persistent fused kernel is compiled for (SRPS_PF_MINB)
@@ -165,6 +166,7 @@ extern "C" void srps_ctx_destroy(srps_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->cg_graph) cudaGraphExecDestroy(ctx->cg_graph);
+    if (ctx->l2_window_bytes) { cudaCtxResetPersistingL2Cache(); cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0); }
     for (int r = 0; r < MAX_RANKS; r++) {
         if (ctx->peer_planes[r]) cudaIpcCloseMemHandle(ctx->peer_planes[r]);
         if (ctx->connected && r != ctx->rank && r < ctx->world && ctx->comm.peer[r]) cudaIpcCloseMemHandle(ctx->comm.peer[r]);
@@ -235,6 +237,7 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
     cudaDeviceProp dp;
     CK(cudaGetDeviceProperties(&dp, ctx->device));
     ctx->sm_count = dp.multiProcessorCount;
+    const size_t l2_persist_max = (size_t)std::max(dp.persistingL2CacheMaxSize, 0), l2_window_max = (size_t)std::max(dp.accessPolicyMaxWindowSize, 0);
     if (dp.major < 10) return fail(ctx, SRPS_E_INVALID, "this library is built for sm_100a (B200) only");
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto& e : ctx->ev) CK(cudaEventCreate(&e));
@@ -332,10 +335,35 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         long long k = 0;
         auto next = [&]() { return ctx->plane_base + (k++) * g.plane + g.origin(); };
         ctx->z = next(); ctx->r = next(); ctx->p = next(); ctx->y = next(); ctx->e0 = next(); ctx->dz = next(); ctx->dz_new = next();
-        for (int c = 0; c < 3; c++) { ctx->w[c] = next(); ctx->gq[c] = next(); ctx->N[c] = next(); ctx->N_new[c] = next(); ctx->rho[c] = next(); }
+        for (int c = 0; c < 3; c++) ctx->w[c] = next();               // contiguous: one L2 access-policy window covers the three (cg_l2_window)
+        for (int c = 0; c < 3; c++) { ctx->gq[c] = next(); ctx->N[c] = next(); ctx->N_new[c] = next(); ctx->rho[c] = next(); }
         ctx->p2 = next();
         ctx->r2 = next(); ctx->y2 = next();
         if (refcg) for (int c = 0; c < 3; c++) { ctx->ad[c] = next(); ctx->ar[c] = next(); ctx->ap[c] = next(); }
+    }
+    // Persisting-L2 window over the weight planes (rho_c/dz)^2 -- the 12 of the 44 bytes per pixel and pass that do not
+    // change during a solve -- attached to the CG launches only (cg_l2_window).  Default rule: when the three planes fit
+    // 3/4 of the set-aside the device allows (79 MiB on B200) while the CG working set (10.25 planes) does not fit the L2,
+    // i.e. 4.2 M pixels per GPU = config 4 on 4 GPUs.  Measured (round 2, that slab on one GPU, persistent fused CG):
+    // 4.02 against 4.15 ms; 2 M pixels (everything L2-resident anyway: 87 % hit rate): 1.93 against 1.88 ms; a set-aside
+    // the window does not fill starves the streams: 79 MiB at 4096^2 (hit ratio 0.62) 33.3 against 14.3 ms.
+    // SRPS_L2_PERSIST=<MiB>|max|0 overrides.
+    {
+        const size_t win = sizeof(float) * (size_t)(3 * g.plane);
+        const size_t l2_bytes = (size_t)std::max(dp.l2CacheSize, 0);
+        size_t want = 0;
+        if (const char* lp = getenv("SRPS_L2_PERSIST"))
+            want = strcmp(lp, "max") == 0 ? l2_persist_max : std::min((size_t)atoll(lp) << 20, l2_persist_max);
+        else if (win <= l2_persist_max / 4 * 3 && win <= l2_window_max && sizeof(float) * (size_t)g.plane * 41 / 4 > l2_bytes)
+            want = win;
+        if (want > 0 && win > 0 && l2_window_max > 0) {
+            CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+            ctx->l2_window_bytes = std::min(win, l2_window_max);
+            ctx->l2_hit_ratio = std::min(1.f, (float)((double)want / (double)ctx->l2_window_bytes));
+        }
+        if (getenv("SRPS_VERBOSE"))
+            fprintf(stderr, "[srps] L2 persisting: device max %zu MiB, window max %zu MiB, set aside %zu MiB, window %zu MiB, hit ratio %.2f\n",
+                    l2_persist_max >> 20, l2_window_max >> 20, want >> 20, ctx->l2_window_bytes >> 20, ctx->l2_hit_ratio);
     }
     if (refcg) {
         CK(cudaMalloc(&ctx->U, sizeof(float) * (size_t)(15 * g.plane)));
@@ -392,11 +420,12 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         const char* cgm = getenv("SRPS_CG");
         // Measured (round 1): a persistent single-launch CG wins on small single-GPU scenes (two-barrier form: Mitten 1.35 vs
         // 1.52 ms, 1080p 2.62 vs 2.95 ms per outer iteration; fused one-barrier form: Mitten 1.11 ms) and loses at 4096^2
-        // (17.7 vs 15.4 ms of CG).  Default: below 3 M pixels PER GPU the persistent fused form (cg_persistent_fused_kernel;
+        // (17.7 vs 15.4 ms of CG); round 2, 4.2 M pixels per GPU (config 4 on 4 GPUs): 5.65 vs 5.93 ms per outer iteration, the
+        // same slab on one GPU 4.93 vs 5.23 ms.  Default: below 6 M pixels PER GPU the persistent fused form (cg_persistent_fused_kernel;
         // with a strip partition its barrier carries the cross-GPU reduction), otherwise one fused kernel per pass
         // (cg_fused_kernel; 4096^2: 14.1 ms against 15.5 ms for operator + update, and one cross-GPU reduction per pass
         // instead of two).  SRPS_CG = persistent_fused | persistent | fused | graph overrides.
-        const bool small = npix < 3000000;
+        const bool small = npix < 6000000;
         const bool want_pf = cgm ? strcmp(cgm, "persistent_fused") == 0 : small;
         const bool want_p = cgm && strcmp(cgm, "persistent") == 0;
         int occ_p = 0;
@@ -942,6 +971,16 @@ static int launch_cg_fused(srps_ctx* ctx, StencilArgs sa, int passes) {
     return 0;
 }
 
+static cudaAccessPolicyWindow cg_l2_window(srps_ctx* ctx, bool on) {
+    cudaAccessPolicyWindow w{};
+    w.base_ptr = (void*)(ctx->w[0] - ctx->g.origin());
+    w.num_bytes = on ? ctx->l2_window_bytes : 0;
+    w.hitRatio = on ? ctx->l2_hit_ratio : 0.f;
+    w.hitProp = on ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+    w.missProp = on ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
+    return w;
+}
+
 // Everything of the depth update is enqueued on the context's stream; the energy terms and the CG scalars are copied to
 // the pinned history slot `slot` (no host synchronisation here).
 static int depth_enqueue(srps_ctx* ctx, int slot) {
@@ -983,6 +1022,11 @@ static int depth_enqueue(srps_ctx* ctx, int slot) {
     ua.comm = ctx->comm;
     const int passes = ctx->h_sc[0].max_iter + 1;     // k <= max_iter -> max_iter + 1 passes   devicecalls.cu:252
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (ctx->l2_window_bytes) {
+        cudaStreamAttrValue v{};
+        v.accessPolicyWindow = cg_l2_window(ctx, true);
+        CK(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &v));
+    }
     if (ctx->use_persistent && !getenv("SRPS_TRACE")) {
         PersistentArgs pa{};
         pa.st = sa; pa.pp[0] = ctx->p; pa.pp[1] = ctx->p2; pa.x = ctx->z; pa.r = ctx->r; pa.n4 = ctx->n4;
@@ -1027,6 +1071,19 @@ static int depth_enqueue(srps_ctx* ctx, int slot) {
             if (ctx->use_fused) launch_cg_fused(ctx, sa, passes); else launch_cg_iterations(ctx, sa, ua, passes);
             CK(cudaStreamEndCapture(ctx->stream, &graph));
             ctx->launches = before;
+            if (ctx->l2_window_bytes) {                     // the window is a kernel-node attribute in a graph
+                size_t nn = 0;
+                CK(cudaGraphGetNodes(graph, nullptr, &nn));
+                std::vector<cudaGraphNode_t> nodes(nn);
+                CK(cudaGraphGetNodes(graph, nodes.data(), &nn));
+                cudaKernelNodeAttrValue v{};
+                v.accessPolicyWindow = cg_l2_window(ctx, true);
+                for (cudaGraphNode_t nd : nodes) {
+                    cudaGraphNodeType ty;
+                    CK(cudaGraphNodeGetType(nd, &ty));
+                    if (ty == cudaGraphNodeTypeKernel) CK(cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributeAccessPolicyWindow, &v));
+                }
+            }
             CK(cudaGraphInstantiate(&ctx->cg_graph, graph, 0));
             CK(cudaGraphDestroy(graph));
         }
@@ -1035,6 +1092,11 @@ static int depth_enqueue(srps_ctx* ctx, int slot) {
     } else {
         if (ctx->use_fused) launch_cg_fused(ctx, sa, passes); else launch_cg_iterations(ctx, sa, ua, passes);
         CK(cudaGetLastError());
+    }
+    if (ctx->l2_window_bytes) {
+        cudaStreamAttrValue v{};
+        v.accessPolicyWindow = cg_l2_window(ctx, false);
+        CK(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &v));
     }
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
     // energy with lagged A,B and the new z (devicecalls.cu:762-767) + the normals of the new z

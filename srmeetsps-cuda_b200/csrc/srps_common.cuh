@@ -142,19 +142,21 @@ __device__ __forceinline__ bool grid_reduce_last(double v, double* partials, uns
 }
 
 // Sum of partials[b * stride + off], b = lane, lane + 32, ... < n, in that order (the fixed order every reduction of
-// this library uses), with eight independent L2 loads in flight per lane: the final sum of a single-pass grid
-// reduction sits on the critical path of every CG pass.
+// this library uses), with sixteen independent L2 loads in flight per lane -- one round trip for the <= 512 blocks of a
+// resident grid: the final sum of a single-pass grid reduction sits on the critical path of every CG pass (ncu, round 2,
+// 512-line slab: 14 % of the warp samples of the persistent kernel waited on these adds with eight in flight).
 __device__ __forceinline__ double lane_strided_sum(const double* partials, int n, int stride, int off, int lane) {
+    constexpr int U = 16;
     double acc = 0.0;
-    for (int b0 = 0; b0 < n; b0 += 32 * 8) {
-        double v[8];
+    for (int b0 = 0; b0 < n; b0 += 32 * U) {
+        double v[U];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < U; u++) {
             const int b = b0 + u * 32 + lane;
             v[u] = b < n ? __ldcg(partials + (long long)b * stride + off) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 8; u++) acc += v[u];      // adding 0.0 for b >= n leaves the sum unchanged
+        for (int u = 0; u < U; u++) acc += v[u];      // adding 0.0 for b >= n leaves the sum unchanged
     }
     return acc;
 }
