@@ -1,9 +1,10 @@
 #!/bin/bash
-# Run ON the GPU box (gpurun, ONE GPU): full ncu capture of the persistent fused CG kernel on the per-GPU slabs of config 4
-# at 4 and 8 GPUs (bench.py workloads n8sim / slab8 on one GPU: no exchange), where the solve is one cooperative launch.
+# Run ON the GPU box (gpurun, ONE GPU): full ncu capture of the persistent fused CG kernel (the default driver: the whole
+# solve is one cooperative launch) on config 4 itself and on its per-GPU slabs at 4 and 8 GPUs (bench.py workloads
+# n8sim / slab8 on one GPU: no exchange).  `python profiles/summarize.py r2` turns the raw pages into the tracked summaries.
 tag=${1:-r2}
 mkdir -p gpurun_out
-for w in slab8 n8sim; do
+for w in ${2:-4k slab8 n8sim}; do
     SRPS_CG=persistent_fused ncu --set full --clock-control none --import-source on -k regex:"cg_persistent_fused_kernel" -s 2 -c 1 -f -o /tmp/${tag}_pf_$w \
         python bench.py --workload $w --steps 2 --warmup 1 --no-cpu --no-extras > gpurun_out/${tag}_under_ncu_pf_$w.log 2>&1
     ncu -i /tmp/${tag}_pf_$w.ncu-rep --page details > gpurun_out/${tag}_pf_${w}_details.txt 2>/dev/null

@@ -66,7 +66,7 @@ out = [f"# ncu --set full --clock-control none --import-source on, SRPS_NO_GRAPH
 seen = set()
 traffic = {}
 sources = []
-for name in ("fused", "stack", "tma"):
+for name in ("fused", "stack", "tma", "pf_4k", "pf_n8sim", "pf_slab8"):
     path = os.path.join(src, f"{tag}_{name}_raw.csv")
     if os.path.exists(path):
         sources.append((f"{tag}_{name}_raw.csv", open(path, errors="ignore").read()))
@@ -85,6 +85,8 @@ for name, raw in sources:
         if len(r) < len(hdr):
             continue
         k = r[idx["Kernel Name"]]
+        if "_pf_" in name:          # the same kernel on three workloads: keep them apart
+            k += {"pf_4k": "  @4096x4096", "pf_n8sim": "  @4096x1024 (4-GPU slab)", "pf_slab8": "  @4096x512 (8-GPU slab)"}[name[len(tag) + 1:-len("_raw.csv")]]
         if k in seen:
             continue
         seen.add(k)
@@ -102,7 +104,7 @@ if seen:
     open(os.path.join(dst, f"{tag}_ncu_full_summary.txt"), "w").write("\n".join(out))
     print("wrote", f"{tag}_ncu_full_summary.txt", len(seen), "kernels")
     import json
-    key = {"cg_fused_kernel<4, 0": "cg_fused", "cg_fused_tma_kernel<4": "cg_fused_tma", "stencil_strip_kernel<0, 4>": "cg_operator",
+    key = {"cg_persistent_fused_kernel<4, 1, 3, 128>(PersistentArgs)  @4096x4096": "cg_persistent_fused", "cg_fused_kernel<4, 0": "cg_fused", "cg_fused_tma_kernel<4": "cg_fused_tma", "stencil_strip_kernel<0, 4>": "cg_operator",
            "cg_update_kernel": "cg_update", "stack_project_kernel<1": "project_pass", "lighting_reduce_kernel": "lighting_pass"}
     tpath = os.path.join(dst, "traffic.json")
     old = json.load(open(tpath)) if os.path.exists(tpath) else {}
@@ -118,7 +120,8 @@ if seen:
     print(json.dumps(t4k))
 # the exported details / top-stall source lines travel as they are
 import shutil
-for name in ("fused_details.txt", "tma_details.txt", "stack_details.txt", "fused_source_top.csv", "tma_source_top.csv"):
+for name in ("fused_details.txt", "tma_details.txt", "stack_details.txt", "fused_source_top.csv", "tma_source_top.csv",
+             "pf_4k_details.txt", "pf_n8sim_details.txt", "pf_slab8_details.txt", "pf_4k_source_top.csv", "pf_n8sim_source_top.csv", "pf_slab8_source_top.csv"):
     p = os.path.join(src, f"{tag}_{name}")
     if os.path.exists(p) and os.path.getsize(p) > 0:
         shutil.copy(p, os.path.join(dst, f"{tag}_ncu_{name}"))

@@ -418,15 +418,14 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         int coop = 0;
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
         const char* cgm = getenv("SRPS_CG");
-        // Measured (round 1): a persistent single-launch CG wins on small single-GPU scenes (two-barrier form: Mitten 1.35 vs
-        // 1.52 ms, 1080p 2.62 vs 2.95 ms per outer iteration; fused one-barrier form: Mitten 1.11 ms) and loses at 4096^2
-        // (17.7 vs 15.4 ms of CG); round 2, 4.2 M pixels per GPU (config 4 on 4 GPUs): 5.65 vs 5.93 ms per outer iteration, the
-        // same slab on one GPU 4.93 vs 5.23 ms.  Default: below 6 M pixels PER GPU the persistent fused form (cg_persistent_fused_kernel;
-        // with a strip partition its barrier carries the cross-GPU reduction), otherwise one fused kernel per pass
-        // (cg_fused_kernel; 4096^2: 14.1 ms against 15.5 ms for operator + update, and one cross-GPU reduction per pass
-        // instead of two).  SRPS_CG = persistent_fused | persistent | fused | graph overrides.
-        const bool small = npix < 6000000;
-        const bool want_pf = cgm ? strcmp(cgm, "persistent_fused") == 0 : small;
+        // Default: the persistent fused form (cg_persistent_fused_kernel: the whole solve is one cooperative launch, one grid
+        // barrier per pass, which with a strip partition also carries the cross-GPU reduction).  Measured (round 2, ms per
+        // outer iteration against one cg_fused_kernel launch per pass in a graph): config 4 on 1 / 2 / 4 GPUs 16.51 / 9.59 /
+        // 5.53 against 16.92 / 9.84 / 5.93, its 4- and 8-GPU slabs on one GPU 4.93 / 2.36 against 5.23 / 2.48, 1080p 2.19
+        // against 2.95 (round 1), Mitten 1.04 against 1.52.  (Round 1's two-barrier persistent form lost at 4096^2,
+        // 17.7 against 15.4 ms of CG, and is kept as SRPS_CG=persistent.)  SRPS_CG = persistent_fused | persistent | fused |
+        // fused_tma | graph overrides; without cooperative launch the fused graph form is used.
+        const bool want_pf = cgm ? strcmp(cgm, "persistent_fused") == 0 : true;
         const bool want_p = cgm && strcmp(cgm, "persistent") == 0;
         int occ_p = 0;
         if (want_p && ctx->use_strip && coop && ctx->world == 1) {
