@@ -221,9 +221,9 @@ def test_each_iteration_from_synchronised_state(cfg, albedo_mode, stencil, monke
     (s, rho, z -> normals), so nothing accumulates; one pass of the loop body must then agree to
     fp32 round-off: depth rel. RMSE <= 2e-5, albedo max-abs <= 3e-4, energy 2e-3, same CG pass count.
     Six CG drivers: one persistent cooperative kernel per solve, the two-kernel CUDA graph with the warp-strip
-    operator, the same with the shared-memory tile operator, the fused one-kernel-per-pass form (default on large
-    scenes), the fused form inside one cooperative launch (default on small scenes) and the fused pass fed by bulk
-    async copies through a shared-memory ring (fused_tma); sf 8/16 scenes fall back to the tile operator in every case."""
+    operator, the same with the shared-memory tile operator, the fused one-kernel-per-pass form, the fused form inside
+    one cooperative launch (the default) and the fused pass fed by bulk async copies through a shared-memory ring
+    (fused_tma); sf 8/16 scenes fall back to the tile operator in every case."""
     monkeypatch.setenv("SRPS_STENCIL", "tile" if stencil == "tile" else "strip")
     monkeypatch.setenv("SRPS_CG", stencil if stencil in ("persistent", "fused", "persistent_fused", "fused_tma") else "graph")
     sc = scene(cfg)
@@ -248,6 +248,29 @@ def test_each_iteration_from_synchronised_state(cfg, albedo_mode, stencil, monke
         # the energy inherits the lighting null-space noise (fp64 vs fp32 oracle differ by 1.4e-3 on the sf=1 scene)
         assert abs(e_gpu - e_ref) <= 2e-3 * abs(e_ref), (it, e_gpu, e_ref)
     ctx.close()
+
+
+@pytest.mark.parametrize("switch", [("SRPS_L2_PERSIST", "8"), ("SRPS_L2_PERSIST", "max"), ("SRPS_CHUNKS", "spread")])
+def test_launch_switches_do_not_change_results(switch, monkeypatch):
+    """The persisting-L2 window over the weight planes (attached to the CG launches; automatic at 4.2 M pixels per GPU) is
+    a cache hint: bit-identical results.  The chunk table with one chunk per warp (SRPS_CHUNKS=spread) regroups the
+    partial sums of the dot products: same pass counts, depth within 1e-6."""
+    cfg = dict(h=96, w=160, sf=4, n=6, seed=31, mask_kind="ellipse")
+    sc = scene(cfg)
+    outs = []
+    for on in (False, True):
+        if on:
+            monkeypatch.setenv(*switch)
+        ctx = make_ctx(sc)
+        ks = [ctx.outer_iteration()[1] for _ in range(3)]
+        outs.append((ks, ctx.download("z"), ctx.download("rho")))
+        ctx.close()
+    (k0, z0, r0), (k1, z1, r1) = outs
+    assert k0 == k1
+    if switch[0] == "SRPS_L2_PERSIST":
+        assert np.array_equal(z0, z1) and np.array_equal(r0, r1)
+    else:
+        assert rel_rmse(z1, z0) <= 1e-6 and np.abs(r1 - r0).max() <= 1e-4
 
 
 def test_mitten_matches_oracle(mitten_scene):
