@@ -444,7 +444,7 @@ def run_ours(args, rank, world, local):
         ctx.outer_iteration()
     # per-phase split and pass counts: a few separately synchronised iterations (srps_outer_iteration returns after each)
     phases = {"ms_lighting": [], "ms_albedo": [], "ms_depth": [], "ms_normals": [], "ms_depth_cg": []}
-    cg_iters, per_call = [], []
+    cg_iters, per_call, zskips = [], [], []
     for _ in range(min(3, max(1, args.steps))):
         _, k = ctx.outer_iteration()
         t = ctx.timings()
@@ -452,6 +452,7 @@ def run_ours(args, rank, world, local):
         for key in phases:
             phases[key].append(t[key])
         cg_iters.append(k)
+        zskips.append(t["cg_zskip"])
     # the timed region: EXACTLY K outer iterations through srps_run(fixed_iters=K) -- the loop the library itself runs,
     # iterations queued back to back -- between two CUDA events on the context's stream, barrier + synchronise on both sides
     sampler = ClockSampler(local)
@@ -489,12 +490,14 @@ def run_ours(args, rank, world, local):
     fused = prof["cg_driver"] in ("fused", "persistent_fused")
     passes = float(np.mean(cg_iters))
     ms_cg = float(np.mean(phases["ms_depth_cg"]))
+    zskip = float(np.mean(zskips))
     if prof["cg_driver"] == "persistent_fused":
         # the whole solve is ONE cooperative launch: its duration is the device time between the events around it in the
-        # timed region (ms_depth_cg), its algorithmic bytes those of the passes it ran
-        kernel = ("cg_persistent_fused_kernel<sf> (whole CG solve in one launch; per pass: r -= alpha y; z += alpha p; p <- r + beta p; "
-                  "y <- (KtK + GtMG) p; r.r, p.y, r.y, y.y; one grid barrier)")
-        alg_bytes, ms_kernel, tkey = 44.0 * npix * passes, ms_cg, "cg_persistent_fused"
+        # timed region (ms_depth_cg), its algorithmic bytes those of the passes it ran: 44 B per pixel, 36 in the passes
+        # that leave z to the next one (srps_timings.cg_zskip)
+        kernel = ("cg_persistent_fused_kernel<sf> (whole CG solve in one launch; per pass: r -= alpha y; p <- r + beta p; "
+                  "y <- (KtK + GtMG) p; r.r, p.y, r.y, y.y; one grid barrier; z += two steps in every other pass)")
+        alg_bytes, ms_kernel, tkey = (44.0 * passes - 8.0 * zskip) * npix, ms_cg, "cg_persistent_fused"
     elif fused:    # one kernel per pass: reads r, y, p, z, w0..2 ; writes r, p, y, z  
         kernel = "cg_fused_kernel<sf> (CG pass: r -= alpha y; z += alpha p; p <- r + beta p; y <- (KtK + GtMG) p; r.r, p.y, r.y, y.y)"
         alg_bytes, ms_kernel, tkey = 44.0 * npix, prof["cg_fused"], "cg_fused"
@@ -512,13 +515,14 @@ def run_ours(args, rank, world, local):
                 traffic = json.load(fh).get(args.workload, {}).get(tkey)
         except Exception:
             pass
-    pass_bytes = 44.0 if fused else 52.0
+    pass_bytes = ((44.0 * passes - 8.0 * zskip) / passes if prof["cg_driver"] == "persistent_fused" else 44.0) if fused else 52.0
     roofline = {"bound": "hbm", "kernel": kernel,
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel, 1 GPU)" if traffic else None,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_kernel, "passes_per_launch": passes if tkey == "cg_persistent_fused" else 1,
+                "passes_without_z": zskip if tkey == "cg_persistent_fused" else 0,
                 "cg_driver": prof["cg_driver"],
                 "other_kernels": {
                     "stencil_strip_kernel (two-kernel form)": {"ms": prof["cg_stencil"], "GBps": 28.0 * npix / (prof["cg_stencil"] * 1e-3) / 1e9},

@@ -79,7 +79,8 @@ typedef struct srps_timings {
     int albedo_cg_iters[3];
     long long launches;          /* kernels launched by this context since creation */
     int cg_deferred;             /* fused CG: passes of the last depth solve that measured r.r instead of expanding it */
-    int pad_;
+    int cg_zskip;                /* persistent fused CG: passes of the last depth solve that left the depth untouched (its step is
+                                    applied together with the next one: 36 instead of 44 bytes per pixel in those passes) */
 } srps_timings;
 
 /* Context: replaces cudaSetDevice + handle creation + all one-shot device setup of

@@ -26,7 +26,7 @@ class Timings(C.Structure):
     _fields_ = [("ms_lighting", C.c_float), ("ms_albedo", C.c_float), ("ms_depth", C.c_float),
                 ("ms_normals", C.c_float), ("ms_total", C.c_float), ("ms_depth_cg", C.c_float),
                 ("cg_iters", C.c_int), ("albedo_cg_iters", C.c_int * 3), ("launches", C.c_longlong),
-                ("cg_deferred", C.c_int), ("pad_", C.c_int)]
+                ("cg_deferred", C.c_int), ("cg_zskip", C.c_int)]
 
 
 EXPORTS = {

@@ -171,7 +171,7 @@ class Context:
         self._ck(self.lib.srps_get_timings(self._ctx, C.byref(t)), "srps_get_timings")
         return dict(ms_lighting=t.ms_lighting, ms_albedo=t.ms_albedo, ms_depth=t.ms_depth, ms_normals=t.ms_normals,
                     ms_total=t.ms_total, ms_depth_cg=t.ms_depth_cg, cg_iters=t.cg_iters,
-                    albedo_cg_iters=list(t.albedo_cg_iters), launches=int(t.launches), cg_deferred=int(t.cg_deferred))
+                    albedo_cg_iters=list(t.albedo_cg_iters), launches=int(t.launches), cg_deferred=int(t.cg_deferred), cg_zskip=int(t.cg_zskip))
 
     def synchronize(self):
         self._ck(self.lib.srps_synchronize(self._ctx), "srps_synchronize")

@@ -1040,6 +1040,7 @@ static int depth_enqueue(srps_ctx* ctx, int slot) {
         PersistentArgs pa{};
         pa.st = sa; pa.pp[0] = ctx->p; pa.pp[1] = ctx->p2; pa.x = ctx->z; pa.r = ctx->r; pa.n4 = ctx->n4;
         pa.passes = passes;
+        { const char* zl = getenv("SRPS_ZLAZY"); pa.zlazy = !(zl && zl[0] == '0'); }     // lazy z (strip_pass, ZL): on unless SRPS_ZLAZY=0
         pa.bar = ctx->sync_words; pa.world_gen = ctx->sync_words + 1; pa.world_tot = (double*)(ctx->sync_words + 2);
         pa.rr[0] = ctx->r; pa.rr[1] = ctx->r2; pa.yy[0] = ctx->y; pa.yy[1] = ctx->y2;
         pa.part[0] = ctx->partials; pa.part[1] = ctx->partials + 4ll * ctx->grid_persistent;
@@ -1130,6 +1131,7 @@ static void depth_collect(srps_ctx* ctx, int slot, float* energy, int* cg_iters)
     ctx->h_energy[0] = hs.energy[0]; ctx->h_energy[1] = hs.energy[1];
     ctx->tm.cg_iters = hs.sc.k;
     ctx->tm.cg_deferred = hs.sc.n_defer;
+    ctx->tm.cg_zskip = hs.sc.n_zskip;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
     ctx->tm.ms_depth_cg = ms;

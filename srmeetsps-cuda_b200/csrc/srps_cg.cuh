@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(CG_NT, 3) stencil_kernel(const StencilArgs a) 
         if (threadIdx.x == 0) {
             CgScalars* s = a.sc;
             if (MODE == MODE_INIT) {                 // r1 = b.b ; k = 0          devicecalls.cu:242-252
-                s->r1 = total; s->r0 = 0.0; s->k = 0; s->beta = 0.f; s->alpha = 0.f; s->defer = 0; s->n_defer = 0;
+                s->r1 = total; s->r0 = 0.0; s->k = 0; s->beta = 0.f; s->alpha = 0.f; s->defer = 0; s->n_defer = 0; s->n_zskip = 0;
                 s->active = ((float)total > s->tol2) && (0 <= s->max_iter);
             } else {                                 // alpha = r1 / (p.Ap)       devicecalls.cu:268-269
                 s->dot = total;
@@ -390,9 +390,15 @@ __device__ __forceinline__ LineQ line_q(const LightConsts& lc, float fx, float f
 // tagged tag_in + 1, and -- MODE_FUSED -- the ghost lines of r and y_in are read from this rank's LL buffer (tag_in)
 // instead of being pulled from the neighbours' planes; MODE_FUSED0 (first pass of a solve) still pulls r, which the
 // residual kernel wrote and ordered with its system-scope reduction.
-template <int MODE, int SF, int COH = 0, bool LLG = false, int NT = SW_NT>
+// ZL (lazy z, persistent fused CG only): the depth is not touched in every pass.  A pass either skips z (`zskip`: no load,
+// no store, the step stays pending) or adds `zc1 p_in + zc2 r_in`, which with zc2 != 0 applies TWO pending steps at once:
+// the older one belongs to the direction before p_in, recovered as (p_in - r_in) / beta_prev from the two operands this
+// pass loads anyway (p_in = r_in + beta_prev p_before was formed from exactly these stored values).  See
+// cg_persistent_fused_kernel for the schedule; 44 -> 36 / 44 B per pixel in alternate passes.
+template <int MODE, int SF, int COH = 0, bool LLG = false, int NT = SW_NT, bool ZL = false>
 __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightConsts& lc, float beta, float alpha = 0.f,
-                                             double* extra = nullptr /* FUSED: r.r, y_in.p, y.y */, unsigned tag_in = 0u) {
+                                             double* extra = nullptr /* FUSED: r.r, y_in.p, y.y */, unsigned tag_in = 0u,
+                                             float zc1 = 0.f, float zc2 = 0.f, bool zskip = false) {
     static_assert(MODE == MODE_ITER || MODE == MODE_APPLY || MODE == MODE_FUSED || MODE == MODE_FUSED0,
                   "the warp-strip kernel implements ITER, APPLY and the fused pass");
     constexpr bool FUSED = (MODE == MODE_FUSED || MODE == MODE_FUSED0);
@@ -456,6 +462,8 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
             rn = make_float4(r4.x - alpha * y4.x, r4.y - alpha * y4.y, r4.z - alpha * y4.z, r4.w - alpha * y4.w);
             const float4 pn = make_float4(rn.x + beta * pin.x, rn.y + beta * pin.y, rn.z + beta * pin.z, rn.w + beta * pin.w);
             ypn = (y4.x * pn.x + y4.y * pn.y) + (y4.z * pn.z + y4.w * pn.w);      // (A p_in).p : the conjugacy defect, see cg_fused_kernel
+            if (ZL)     // `pin` leaves as the z increment of this pass (its only use): both pending steps, see the header
+                pin = make_float4(zc1 * pin.x + zc2 * r4.x, zc1 * pin.y + zc2 * r4.y, zc1 * pin.z + zc2 * r4.z, zc1 * pin.w + zc2 * r4.w);
             return pn;
         };
         // LLG: line -1 (side 0) / ny (side 1) of r and y_in out of this rank's LL ghost buffer; p_in is local
@@ -481,15 +489,19 @@ __device__ __forceinline__ double strip_pass(const StencilArgs& a, const LightCo
         // z is read and written by this kernel (each float4 by its owner only): coherent load, clamped like the others
         auto load_x = [&](int j) -> float4 {
             const bool ok = colok && j <= ny;
-            return ld4(a.x + (ok ? (long long)j * pitch + x : 0));
+            float4 v = f4zero();
+            if (!(ZL && zskip)) v = ld4(a.x + (ok ? (long long)j * pitch + x : 0));      // uniform predicate, no branch region
+            return v;
         };
         // owner's stores of a freshly loaded line: the new residual, the pending z step, and r.r
         auto store_owned = [&](int j, const float4& rn, const float4& xo, const float4& pin, float ypn) {
             if (writer && j < jB) {
                 const long long off = (long long)j * pitch + x;
                 st4(a.r_out + off, rn);
-                if (MODE == MODE_FUSED)
+                if (MODE == MODE_FUSED && !ZL)
                     st4(a.x + off, make_float4(xo.x + alpha * pin.x, xo.y + alpha * pin.y, xo.z + alpha * pin.z, xo.w + alpha * pin.w));
+                if (MODE == MODE_FUSED && ZL && !zskip)
+                    st4(a.x + off, make_float4(xo.x + pin.x, xo.y + pin.y, xo.z + pin.z, xo.w + pin.w));
                 s_rr += (double)((rn.x * rn.x + rn.y * rn.y) + (rn.z * rn.z + rn.w * rn.w));
                 s_yp += (double)ypn;
             }
@@ -793,7 +805,7 @@ __global__ void __launch_bounds__(SW_NT, 2) stencil_strip_init_kernel(const Sten
     if (grid_reduce_last_world<SW_NT>(dot, a.partials, a.ticket, red, total, a.comm)) {
         if (threadIdx.x == 0) {                  // r1 = b.b ; k = 0          devicecalls.cu:242-252
             CgScalars* s = a.sc;
-            s->r1 = total; s->r0 = 0.0; s->k = 0; s->beta = 0.f; s->alpha = 0.f; s->defer = 0; s->n_defer = 0;
+            s->r1 = total; s->r0 = 0.0; s->k = 0; s->beta = 0.f; s->alpha = 0.f; s->defer = 0; s->n_defer = 0; s->n_zskip = 0;
             s->active = ((float)total > s->tol2) && (0 <= s->max_iter);
         }
     }
@@ -919,7 +931,7 @@ constexpr int FUSED_SPARE_PASSES = 2;        // pass slots a solve has for defer
 // thread's share of |r_out|^2.  Element-wise over the owned lines; p is copied on the two ghost / guard lines as well
 // (strip partition: the neighbours' p there is kept redundantly; r and y ghosts are pulled, not stored).
 template <int COH, bool LLG>
-__device__ __forceinline__ double fused_update_only(const StencilArgs& a, float alpha, unsigned tag_in) {
+__device__ __forceinline__ double fused_update_only(const StencilArgs& a, float alpha, unsigned tag_in, float zc1, float zc2 = 0.f) {
     const long long q = a.g.pitch / 4;
     const long long lo = -q, hi = (long long)(a.g.ny + 1) * q, own = (long long)a.g.ny * q;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -931,7 +943,8 @@ __device__ __forceinline__ double fused_update_only(const StencilArgs& a, float 
             const float4 r4 = ld4_coh<(COH ? 1 : 0)>(a.r + 4 * i), y4 = ld4_coh<(COH ? 1 : 0)>(a.y_in + 4 * i);
             float4 x4 = ld4(a.x + 4 * i);
             const float4 rn = make_float4(r4.x - alpha * y4.x, r4.y - alpha * y4.y, r4.z - alpha * y4.z, r4.w - alpha * y4.w);
-            x4.x += alpha * p4.x; x4.y += alpha * p4.y; x4.z += alpha * p4.z; x4.w += alpha * p4.w;
+            // z += zc1 p + zc2 r: zc1 = alpha, zc2 = 0 unless an older step is pending as well (lazy z, see strip_pass)
+            x4.x += zc1 * p4.x + zc2 * r4.x; x4.y += zc1 * p4.y + zc2 * r4.y; x4.z += zc1 * p4.z + zc2 * r4.z; x4.w += zc1 * p4.w + zc2 * r4.w;
             st4(a.r_out + 4 * i, rn);
             st4(a.y + 4 * i, y4);
             st4(a.x + 4 * i, x4);
@@ -1003,7 +1016,7 @@ __global__ void __launch_bounds__(SW_NT, SRPS_FUSED_MINB) cg_fused_kernel(const 
     const bool deferred = !FIRST && a.sc->defer != 0;       // uniform over the grid: written by the previous launch
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     if (deferred) {
-        v[0] = fused_update_only<0, LLG>(a, alpha, tag_in);
+        v[0] = fused_update_only<0, LLG>(a, alpha, tag_in, alpha);
     } else {
         const LightConsts& lc = c_lc[a.lc_slot];
         double ex[3];
@@ -1053,6 +1066,7 @@ struct PersistentArgs {
     float* r;                       // residual (read + written)
     long long n4;
     int passes;                     // max_iter + 1
+    int zlazy;                      // fused form: skip the depth in alternate passes (strip_pass, ZL)
     unsigned long long* bar;        // grid barrier counter, zero on entry
     double* part[2];                // per-block partials: the two reductions of a pass (gridDim.x doubles each) / fused form:
                                     // the four dots of a pass, buffers alternating between passes (4 * gridDim.x doubles each)
@@ -1289,6 +1303,16 @@ __global__ void __launch_bounds__(NT, MINB) cg_persistent_fused_kernel(const Per
     const int max_iter = sc->max_iter;
     double r1 = sc->r1, r0 = 0.0;
     float alpha = 0.f, beta = 0.f;                   // alpha: the step of the previous pass, still pending
+    // Lazy z: `alpha` belongs to the direction the next pass loads as p_in; `alpha_old` (if != 0) to the direction before it,
+    // which that pass recovers as (p_in - r_in) / beta_link.  A pass with nothing older pending may skip z altogether (36
+    // instead of 44 B per pixel); the next one -- a normal pass, a deferred slot, or the tail below -- then applies both
+    // steps.  Not after a tiny beta (the recovery divides by it): such a pass applies its step at once, as does every pass
+    // with a.zlazy == 0.
+    constexpr float ZL_MIN_BETA = 1e-3f;
+    float alpha_old = 0.f, beta_link = 1.f;
+    float t_c1 = 0.f, t_c2 = 0.f;                    // tail: z += t_c1 pp[t_plane] + t_c2 rr[t_plane]
+    int t_plane = 0, n_zskip = 0;
+    bool tail_set = false;
     int k = 0, plane = 0;
     bool deferred = false;
     int n_defer = 0;
@@ -1308,26 +1332,37 @@ __global__ void __launch_bounds__(NT, MINB) cg_persistent_fused_kernel(const Per
             st.y_prev_line = nullptr; st.y_next_line = nullptr;
         }
         const unsigned tag_in = (unsigned)(tag0 + (unsigned long long)pass);
+        // what this pass does to z
+        float zc1 = alpha, zc2 = 0.f;
+        bool zskip = false;
+        if (alpha_old != 0.f) { zc2 = -alpha_old / beta_link; zc1 = alpha - zc2; }            // two steps at once
+        else if (alpha == 0.f) zskip = true;                                                  // nothing pending (first pass, after a deferred slot)
+        else if (a.zlazy && !deferred && beta >= ZL_MIN_BETA) zskip = true;                   // leave it to the next pass
         double v[4] = {0.0, 0.0, 0.0, 0.0};
-        if (deferred) {                              // see cg_fused_kernel: apply the step, measure r.r
-            v[0] = fused_update_only<1, WORLD>(st, alpha, tag_in);
+        if (deferred) {                              // see cg_fused_kernel: apply the step(s), measure r.r
+            v[0] = fused_update_only<1, WORLD>(st, alpha, tag_in, zc1, zc2);
         } else {
             double ex[3];
             v[1] = (pass == 0) ? strip_pass<MODE_FUSED0, SF, 1, WORLD, NT>(st, lc, 0.f, 0.f, ex, tag_in)
-                               : strip_pass<MODE_FUSED, SF, 1, WORLD, NT>(st, lc, beta, alpha, ex, tag_in);
+                               : strip_pass<MODE_FUSED, SF, 1, WORLD, NT, true>(st, lc, beta, alpha, ex, tag_in, zc1, zc2, zskip);
             v[0] = ex[0]; v[2] = ex[1]; v[3] = ex[2];
         }
         grid_allreduce4<WORLD, NT>(a, v, pass & 1, gen, wsm, s_tot, (unsigned long long)tag0 + (unsigned long long)pass + 1ull);
         const double S0 = v[0], S1 = v[1], S3 = v[3];
         if (!((float)S0 > tol2)) {                   // void pass, see cg_fused_kernel
             r1 = S0;
+            // a void pass cancels its own step; if it skipped z, the step it ran with is still owed (its p_in plane is intact)
+            tail_set = true;
+            t_plane = pass & 1;
+            t_c1 = (zskip && !deferred) ? alpha : 0.f;
+            t_c2 = 0.f;
             alpha = 0.f;
             break;
         }
         if (deferred) {
             beta = (float)S0 / (float)r0;                                         // devicecalls.cu:262, r.r measured
             r1 = S0;
-            alpha = 0.f;
+            alpha = 0.f; alpha_old = 0.f;            // the slot applied everything that was pending
             deferred = false;
             n_defer++;
             continue;
@@ -1337,24 +1372,37 @@ __global__ void __launch_bounds__(NT, MINB) cg_persistent_fused_kernel(const Per
         const double rr = S0 - 2.0 * (double)al * S2 + (double)al * (double)al * S3;
         deferred = !(rr > FUSED_DEFER_REL * S0);
         r0 = S0; r1 = rr;
+        if (zskip && alpha != 0.f) { alpha_old = alpha; beta_link = beta; n_zskip++; }      // p_out = r_out + beta p_in links the two directions
+        else alpha_old = 0.f;
         beta = deferred ? 0.f : (float)rr / (float)S0;                            // devicecalls.cu:262
         alpha = al;
         k++;
         plane = (pass + 1) & 1;
         if (!(k <= max_iter)) break;                                              // devicecalls.cu:252 (k part)
     }
-    if (alpha != 0.f) {                              // z += alpha p of the last valid pass (the last barrier ordered p)
-        const float* p = a.pp[plane];
+    if (!tail_set) {                                 // the step(s) still pending after the last valid pass (the last barrier ordered p, r)
+        t_plane = plane;
+        t_c2 = (alpha_old != 0.f) ? -alpha_old / beta_link : 0.f;
+        t_c1 = alpha - t_c2;
+    }
+    if (t_c1 != 0.f || t_c2 != 0.f) {
+        const float* p = a.pp[t_plane];
+        const float* r = a.rr[t_plane];
         const long long stride = (long long)gridDim.x * NT;
         for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < a.n4; i += stride) {
             const float4 p4 = __ldcg(reinterpret_cast<const float4*>(p + 4 * i));
             float4 x4 = ld4(a.x + 4 * i);
-            x4.x += alpha * p4.x; x4.y += alpha * p4.y; x4.z += alpha * p4.z; x4.w += alpha * p4.w;
+            if (t_c2 != 0.f) {
+                const float4 r4 = __ldcg(reinterpret_cast<const float4*>(r + 4 * i));
+                x4.x += t_c1 * p4.x + t_c2 * r4.x; x4.y += t_c1 * p4.y + t_c2 * r4.y; x4.z += t_c1 * p4.z + t_c2 * r4.z; x4.w += t_c1 * p4.w + t_c2 * r4.w;
+            } else {
+                x4.x += t_c1 * p4.x; x4.y += t_c1 * p4.y; x4.z += t_c1 * p4.z; x4.w += t_c1 * p4.w;
+            }
             st4(a.x + 4 * i, x4);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        sc->r1 = r1; sc->r0 = r0; sc->k = k; sc->beta = beta; sc->alpha = 0.f; sc->defer = 0; sc->n_defer = n_defer;
+        sc->r1 = r1; sc->r0 = r0; sc->k = k; sc->beta = beta; sc->alpha = 0.f; sc->defer = 0; sc->n_defer = n_defer; sc->n_zskip = n_zskip;
         sc->active = 0;
     }
 }

@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(SW_NT, SRPS_TMA_MINB) cg_fused_tma_kernel(cons
     const unsigned tag_in = LLG ? (unsigned)__ldcg(a.comm.seq) : 0u;
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     if (deferred) {
-        v[0] = fused_update_only<0, LLG>(a, alpha, tag_in);
+        v[0] = fused_update_only<0, LLG>(a, alpha, tag_in, alpha);
     } else {
         const LightConsts& lc = c_lc[a.lc_slot];
         double ex[3];

@@ -54,6 +54,7 @@ struct CgScalars {
                       // step and MEASURES r.r, beta comes from the measurement (see cg_fused_kernel)
     int profile;      // srps_profile_kernels: keep the scalars as set by the host (timing of one pass in isolation)
     int n_defer;      // deferred passes of this solve (diagnostics: srps_timings.cg_deferred)
+    int n_zskip;      // persistent fused CG: passes of this solve that left z untouched (srps_timings.cg_zskip)
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }

@@ -250,11 +250,12 @@ def test_each_iteration_from_synchronised_state(cfg, albedo_mode, stencil, monke
     ctx.close()
 
 
-@pytest.mark.parametrize("switch", [("SRPS_L2_PERSIST", "8"), ("SRPS_L2_PERSIST", "max"), ("SRPS_CHUNKS", "spread")])
+@pytest.mark.parametrize("switch", [("SRPS_L2_PERSIST", "8"), ("SRPS_L2_PERSIST", "max"), ("SRPS_CHUNKS", "spread"), ("SRPS_ZLAZY", "0")])
 def test_launch_switches_do_not_change_results(switch, monkeypatch):
     """The persisting-L2 window over the weight planes (attached to the CG launches; automatic at 4.2 M pixels per GPU) is
     a cache hint: bit-identical results.  The chunk table with one chunk per warp (SRPS_CHUNKS=spread) regroups the
-    partial sums of the dot products: same pass counts, depth within 1e-6."""
+    partial sums of the dot products: same pass counts, depth within 1e-6.  SRPS_ZLAZY=0 makes every CG pass apply its
+    depth step at once instead of two steps in every other pass (strip_pass, ZL): the same sum in another order."""
     cfg = dict(h=96, w=160, sf=4, n=6, seed=31, mask_kind="ellipse")
     sc = scene(cfg)
     outs = []
@@ -263,10 +264,11 @@ def test_launch_switches_do_not_change_results(switch, monkeypatch):
             monkeypatch.setenv(*switch)
         ctx = make_ctx(sc)
         ks = [ctx.outer_iteration()[1] for _ in range(3)]
-        outs.append((ks, ctx.download("z"), ctx.download("rho")))
+        outs.append((ks, ctx.download("z"), ctx.download("rho"), ctx.timings()["cg_zskip"]))
         ctx.close()
-    (k0, z0, r0), (k1, z1, r1) = outs
+    (k0, z0, r0, s0), (k1, z1, r1, s1) = outs
     assert k0 == k1
+    assert s0 >= 40 and (s1 == 0 if switch[0] == "SRPS_ZLAZY" else s1 == s0)      # about every other pass of the default run skips z
     if switch[0] == "SRPS_L2_PERSIST":
         assert np.array_equal(z0, z1) and np.array_equal(r0, r1)
     else:
