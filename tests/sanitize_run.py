@@ -15,6 +15,8 @@ SCENES = [dict(h=64, w=96, sf=2, n=6, seed=12, mask_kind="random95"), dict(h=300
           dict(h=48, w=272, sf=8, n=6, seed=6, mask_kind="ellipse"), dict(h=40, w=24, sf=1, n=6, seed=5, mask_kind="random95"),
           dict(h=64, w=50, sf=2, n=5, seed=14, mask_kind="full"), dict(h=40, w=48, sf=1, n=6, seed=5, mask_kind="random95", dark=0.1)]
 DRIVERS = (("strip", "persistent_fused"), ("strip", "persistent"), ("strip", "graph"), ("strip", "fused"), ("strip", "fused_tma"), ("tile", "graph"))
+if os.environ.get("SRPS_SAN_DRIVERS"):          # e.g. SRPS_SAN_DRIVERS=persistent_fused,fused: only these CG drivers
+    DRIVERS = tuple(d for d in DRIVERS if d[1] in os.environ["SRPS_SAN_DRIVERS"].split(",") and d[0] == "strip")
 for cfg in SCENES:
     sc = o.synth_scene(cfg["h"], cfg["w"], cfg["sf"], cfg["n"], seed=cfg["seed"], mask_kind=cfg["mask_kind"])
     if "dark" in cfg:
