@@ -161,12 +161,19 @@ static int publish_lc(srps_ctx* ctx) {
 }
 
 // ------------------------------------------------------------------------------------------------
+constexpr int MAX_L2_DEVICES = 64;
+static std::atomic<int> g_l2_users[MAX_L2_DEVICES];      // contexts per device that hold a persisting-L2 set-aside
+
 extern "C" void srps_ctx_destroy(srps_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->cg_graph) cudaGraphExecDestroy(ctx->cg_graph);
-    if (ctx->l2_window_bytes) { cudaCtxResetPersistingL2Cache(); cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0); }
+    // the L2 set-aside is a device-wide limit: the last context of this device that asked for one gives it back
+    if (ctx->l2_window_bytes && ctx->device >= 0 && ctx->device < MAX_L2_DEVICES && --g_l2_users[ctx->device] == 0) {
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    }
     for (int r = 0; r < MAX_RANKS; r++) {
         if (ctx->peer_planes[r]) cudaIpcCloseMemHandle(ctx->peer_planes[r]);
         if (ctx->connected && r != ctx->rank && r < ctx->world && ctx->comm.peer[r]) cudaIpcCloseMemHandle(ctx->comm.peer[r]);
@@ -357,7 +364,10 @@ static int ctx_create_impl(srps_ctx* ctx, const srps_problem* prob) {
         else if (win <= l2_persist_max / 4 * 3 && win <= l2_window_max && sizeof(float) * (size_t)g.plane * 41 / 4 > l2_bytes)
             want = win;
         if (want > 0 && win > 0 && l2_window_max > 0) {
-            CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+            size_t have = 0;                                 // several contexts on one device: keep the largest request
+            CK(cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize));
+            if (want > have) CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+            if (ctx->device >= 0 && ctx->device < MAX_L2_DEVICES) ++g_l2_users[ctx->device];
             ctx->l2_window_bytes = std::min(win, l2_window_max);
             ctx->l2_hit_ratio = std::min(1.f, (float)((double)want / (double)ctx->l2_window_bytes));
         }
