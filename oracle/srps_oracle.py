@@ -178,7 +178,8 @@ def cg_reference(matvec, x, b, dt=np.float32, max_iter=CG_MAX_ITER, tol=CG_TOL):
     return x, k
 
 
-def cg_fused_reference(matvec, x, b, dt=np.float32, max_iter=CG_MAX_ITER, tol=CG_TOL, defer_rel=1e-6, stats=None):
+def cg_fused_reference(matvec, x, b, dt=np.float32, max_iter=CG_MAX_ITER, tol=CG_TOL, defer_rel=1e-6, stats=None, lazy_z=False,
+                       lazy_min_beta=1e-3):
     """The recurrence of the CUDA path's one-kernel-per-pass CG (csrc/srps_cg.cuh: cg_fused_kernel), restated to
     show that it is the reference's CG (cg_reference above, devicecalls.cu:229-279) in another order of operations:
     pass k first applies the step of pass k-1 (r -= alpha y, x += alpha p), then forms p and y = A p and four dots;
@@ -186,26 +187,42 @@ def cg_fused_reference(matvec, x, b, dt=np.float32, max_iter=CG_MAX_ITER, tol=CG
     from the dots, r.y = p.y - beta (y_prev . p) (A symmetric).  A pass that measures r.r <= tol^2 is void.
     Guard: when the expansion cancels (|r_{k+1}|^2 < defer_rel * r.r) the next pass slot only applies the pending step
     and measures r.r; beta then is the reference's r1/r0 of measured norms.  stats (dict) receives the number of
-    deferred passes."""
+    deferred passes.
+
+    lazy_z=True restates the schedule of cg_persistent_fused_kernel: a pass with only one step pending may leave x
+    untouched; the next slot (pass, deferred slot or tail) applies both steps, the older direction recovered from its
+    own operands as (p_in - r_in) / beta_link.  stats["zskip"] counts the passes that skipped x."""
     f64 = np.float64
     x = x.astype(dt).copy()
     r = b.astype(dt).copy()
     tol2 = dt(tol) * dt(tol)
     k = 0
     alpha = dt(0); beta = dt(0)
+    alpha_old = dt(0); beta_link = dt(1)
     p = np.zeros_like(r); y = np.zeros_like(r)
     active = dt(np.dot(r.astype(f64), r.astype(f64))) > tol2
     deferred = False
-    n_deferred = 0
+    n_deferred = n_zskip = 0
     r0 = 0.0
+    tail = None                          # (c1, c2, p, r) set by a void pass that still owes a step
     slots = max_iter + 1 + 2            # FUSED_SPARE_PASSES
     while active and slots > 0:
         slots -= 1
-        r = (r - alpha * y).astype(dt)
-        x = (x + alpha * p).astype(dt)
+        # what this slot does to x
+        zc1, zc2, zskip = alpha, dt(0), False
+        if alpha_old != 0:
+            zc2 = dt(-alpha_old / beta_link); zc1 = dt(alpha - zc2)
+        elif alpha == 0:
+            zskip = True
+        elif lazy_z and not deferred and beta >= dt(lazy_min_beta):
+            zskip = True
+        r_in, p_in = r, p
+        if not zskip:
+            x = (x + (zc1 * p_in + zc2 * r_in).astype(dt)).astype(dt)
+        r = (r_in - alpha * y).astype(dt)
         if deferred:                     # fused_update_only: p, y unchanged, r.r measured
             S0 = float(np.dot(r.astype(f64), r.astype(f64)))
-            alpha = dt(0)
+            alpha = dt(0); alpha_old = dt(0)
             if not (dt(S0) > tol2):
                 break
             beta = dt(dt(S0) / dt(r0))
@@ -213,26 +230,38 @@ def cg_fused_reference(matvec, x, b, dt=np.float32, max_iter=CG_MAX_ITER, tol=CG
             n_deferred += 1
             continue
         y_prev = y
-        p = (r + beta * p).astype(dt)
+        p = (r + beta * p_in).astype(dt)
         y = matvec(p).astype(dt)
         S0 = float(np.dot(r.astype(f64), r.astype(f64)))
         S1 = float(np.dot(p.astype(f64), y.astype(f64)))
         S3 = float(np.dot(y.astype(f64), y.astype(f64)))
         C = float(np.dot(y_prev.astype(f64), p.astype(f64)))
         if not (dt(S0) > tol2):          # the reference left its loop before this pass
-            alpha = dt(0)
+            if zskip and alpha != 0:     # ... and this pass had left its step to the next one: the tail applies it
+                tail = (alpha, dt(0), p_in, r_in)
+            alpha = dt(0); alpha_old = dt(0)
             break
-        alpha = dt(dt(S0) / dt(S1))
+        al = dt(dt(S0) / dt(S1))
         S2 = S1 - float(beta) * C
-        rr = S0 - 2.0 * float(alpha) * S2 + float(alpha) ** 2 * S3
+        rr = S0 - 2.0 * float(al) * S2 + float(al) ** 2 * S3
         deferred = not (rr > defer_rel * S0)
         r0 = S0
+        if zskip and alpha != 0:
+            alpha_old, beta_link = alpha, beta      # p = r + beta p_in links the two directions
+            n_zskip += 1
+        else:
+            alpha_old = dt(0)
         beta = dt(0) if deferred else dt(dt(rr) / dt(S0))
+        alpha = al
         k += 1
         active = k <= max_iter
-    x = (x + alpha * p).astype(dt)     # the step still pending after the last pass (cg_tail_kernel)
+    if tail is None:                     # the step(s) still pending after the last pass (cg_tail_kernel / the kernel's tail loop)
+        zc2 = dt(-alpha_old / beta_link) if alpha_old != 0 else dt(0)
+        tail = (dt(alpha - zc2), zc2, p, r)
+    x = (x + (tail[0] * tail[2] + tail[1] * tail[3]).astype(dt)).astype(dt)
     if stats is not None:
         stats["deferred"] = n_deferred
+        stats["zskip"] = n_zskip
     return x, k
 
 

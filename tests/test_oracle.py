@@ -169,3 +169,52 @@ def test_fused_cg_guard_measures_when_the_expansion_cancels():
     err_ref = np.linalg.norm(z_ref - sol) / np.linalg.norm(sol)
     err_fus = np.linalg.norm(z_fus - sol) / np.linalg.norm(sol)
     assert err_fus <= 2.0 * err_ref + 1e-6
+
+
+def _spd(rng, n, lam):
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    A = ((Q * lam) @ Q.T).astype(np.float32)
+    return 0.5 * (A + A.T)
+
+
+@pytest.mark.parametrize("max_iter", [0, 1, 2, 3, 4, 7, 100])
+@pytest.mark.parametrize("spectrum", ["spread", "clustered", "identity_like"])
+def test_lazy_depth_update_is_the_eager_one(spectrum, max_iter):
+    """The persistent kernel's lazy z schedule (oracle.cg_fused_reference(lazy_z=True) restates it: every other pass
+    leaves x untouched, the next slot applies both steps with the older direction recovered as (p_in - r_in) / beta)
+    gives the solution of the eager recurrence to fp32 round-off -- for every way a solve can end: iteration limit after an
+    odd / even number of passes (tail with one or two pending steps), early convergence (void pass that had skipped x),
+    deferred slots (clustered spectrum), nothing to do."""
+    rng = np.random.default_rng(7)
+    n = 300
+    lam = {"spread": np.geomspace(1.0, 300.0, n),
+           "clustered": np.concatenate([np.full(n - 3, 1.0), [2.0, 3.0, 5.0]]),
+           "identity_like": 1.0 + 1e-3 * rng.random(n)}[spectrum]
+    A = _spd(rng, n, lam)
+    mv = lambda v: (A @ v.astype(np.float32)).astype(np.float32)
+    x0 = rng.standard_normal(n).astype(np.float32) * np.float32(10.0)        # steps are small against x, as for depths
+    b = rng.standard_normal(n).astype(np.float32)
+    se, sl = {}, {}
+    xe, ke = o.cg_fused_reference(mv, x0, b, np.float32, max_iter=max_iter, stats=se)
+    xl, kl = o.cg_fused_reference(mv, x0, b, np.float32, max_iter=max_iter, stats=sl, lazy_z=True)
+    assert kl == ke and sl["deferred"] == se["deferred"]
+    assert se["zskip"] == 0
+    if ke >= 2 and spectrum == "spread":          # (the other two converge so fast that beta falls below lazy_min_beta)
+        assert sl["zskip"] >= 1, "the schedule must skip x somewhere"
+    step = np.linalg.norm(xe - x0)
+    assert np.linalg.norm(xl - xe) <= 2e-6 * np.linalg.norm(xe) + 1e-5 * step
+
+
+def test_lazy_depth_update_keeps_a_tiny_beta_eager():
+    """The recovery divides by beta: below lazy_min_beta a pass applies its step at once."""
+    rng = np.random.default_rng(3)
+    n = 200
+    A = _spd(rng, n, np.concatenate([np.full(n - 1, 1.0), [1.0 + 1e-2]]))
+    mv = lambda v: (A @ v.astype(np.float32)).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    x0 = np.zeros(n, np.float32)
+    s0, s1 = {}, {}
+    xe, ke = o.cg_fused_reference(mv, x0, b, np.float32, stats=s0, lazy_z=True, lazy_min_beta=10.0)    # never lazy
+    xl, kl = o.cg_fused_reference(mv, x0, b, np.float32, stats=s1, lazy_z=True)
+    assert s0["zskip"] == 0 and ke == kl
+    assert np.linalg.norm(xl - xe) <= 2e-6 * max(np.linalg.norm(xe), 1e-30)
