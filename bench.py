@@ -462,7 +462,8 @@ def run_ours(args, rank, world, local):
     ctx.timer_start()
     energies = ctx.run(fixed_iters=args.steps)
     ms_region = ctx.timer_stop()
-    launches = ctx.timings()["launches"] - l0
+    t_last = ctx.timings()                # per-phase device times of the LAST iteration of the timed region (events inside it)
+    launches = t_last["launches"] - l0
     barrier(world)
     clocks = sampler.stop()
     assert len(energies) == args.steps
@@ -490,14 +491,16 @@ def run_ours(args, rank, world, local):
     fused = prof["cg_driver"] in ("fused", "persistent_fused")
     passes = float(np.mean(cg_iters))
     ms_cg = float(np.mean(phases["ms_depth_cg"]))
+    ms_cg_timed = float(t_last["ms_depth_cg"]) if t_last["ms_depth_cg"] > 0 else ms_cg      # the CG launch of the last timed iteration
     zskip = float(np.mean(zskips))
     if prof["cg_driver"] == "persistent_fused":
-        # the whole solve is ONE cooperative launch: its duration is the device time between the events around it in the
-        # timed region (ms_depth_cg), its algorithmic bytes those of the passes it ran: 44 B per pixel, 36 in the passes
+        # the whole solve is ONE cooperative launch: its duration is the device time between the events around it, taken
+        # from the last iteration of the timed region (the mean over the three separately synchronised iterations before
+        # it is printed next to it); its algorithmic bytes are those of the passes it ran: 44 B per pixel, 36 in the passes
         # that leave z to the next one (srps_timings.cg_zskip)
         kernel = ("cg_persistent_fused_kernel<sf> (whole CG solve in one launch; per pass: r -= alpha y; p <- r + beta p; "
                   "y <- (KtK + GtMG) p; r.r, p.y, r.y, y.y; one grid barrier; z += two steps in every other pass)")
-        alg_bytes, ms_kernel, tkey = (44.0 * passes - 8.0 * zskip) * npix, ms_cg, "cg_persistent_fused"
+        alg_bytes, ms_kernel, tkey = (44.0 * passes - 8.0 * zskip) * npix, ms_cg_timed, "cg_persistent_fused"
     elif fused:    # one kernel per pass: reads r, y, p, z, w0..2 ; writes r, p, y, z  
         kernel = "cg_fused_kernel<sf> (CG pass: r -= alpha y; z += alpha p; p <- r + beta p; y <- (KtK + GtMG) p; r.r, p.y, r.y, y.y)"
         alg_bytes, ms_kernel, tkey = 44.0 * npix, prof["cg_fused"], "cg_fused"
@@ -523,6 +526,7 @@ def run_ours(args, rank, world, local):
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_kernel, "passes_per_launch": passes if tkey == "cg_persistent_fused" else 1,
                 "passes_without_z": zskip if tkey == "cg_persistent_fused" else 0,
+                "ms_per_launch_separately_synchronised": ms_cg if tkey == "cg_persistent_fused" else None,
                 "cg_driver": prof["cg_driver"],
                 "other_kernels": {
                     "stencil_strip_kernel (two-kernel form)": {"ms": prof["cg_stencil"], "GBps": 28.0 * npix / (prof["cg_stencil"] * 1e-3) / 1e9},
